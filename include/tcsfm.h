@@ -1,0 +1,115 @@
+/* tcsfm.h -- C ABI of the fused sm_100a inverse-warp + SSIM/L1 photometric-loss path.
+ *
+ * The reference (utiasSTARS/tightly-coupled-SfM) is pure Python/PyTorch and has no
+ * FFI of its own; its "operator API" for this path is a handful of Python callables.
+ * Each entry point below names the reference callable (file:line, relative to the
+ * reference root) whose arithmetic it replaces.  The Python drop-ins in
+ * tightly-coupled-sfm_b200/{stn,losses,train_mono,pft}.py bind these symbols with
+ * ctypes and keep the reference's call signatures.
+ *
+ * Conventions
+ *  - plain C: device pointers + sizes, no C++/torch types.  All tensors are fp32.
+ *  - images are [B,C,H,W] views with unit W stride and H stride == W; batch and
+ *    channel strides (in elements) are passed explicitly so that channel slices of
+ *    a 6-channel stack (train_mono.py:69 passes imgs[:,3:6]) need no copy.
+ *    depth / mask / per-pixel outputs are contiguous [B,1,H,W].
+ *  - kinv is K^-1 as [B,9] row-major, proj is K @ [R|t] as [B,12] row-major
+ *    (models/stn.py:257,262); they are produced by the caller so that their bits
+ *    are the reference's.
+ *  - every launch goes to `stream` (a cudaStream_t passed as void*); no host
+ *    synchronisation, no allocation, no global state besides the last-error string.
+ *    Buffers documented as "accumulated" are zeroed by the library on `stream`.
+ *  - return value: 0 on success, non-zero on error (message via tcsfm_last_error()).
+ */
+#ifndef TCSFM_H_
+#define TCSFM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCSFM_ABI_VERSION 1
+
+/* ---- flags ------------------------------------------------------------------ */
+/* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
+ * operators differ between devices: CUDA divides by a Python
+ * scalar by multiplying with its fp32 reciprocal and takes mean(dim) as
+ * sum * (1/n); the CPU kernels divide.  Flavour 0 reproduces the CUDA operators
+ * (the reference's production path), flavour 1 the CPU ones (used to compare
+ * bit-for-bit against CPU-generated golden vectors). */
+#define TCSFM_ARITH_CPU        (1 << 0)
+/* pair-loss configuration (losses.py:65-73,151-183 config keys) */
+#define TCSFM_AUTO_MASK        (1 << 1)   /* with_auto_mask   */
+#define TCSFM_SSIM             (1 << 2)   /* l_ssim           */
+#define TCSFM_DEPTH_MASK       (1 << 3)   /* with_depth_mask  */
+#define TCSFM_DEPTH_CONSIST    (1 << 4)   /* l_depth_consist  */
+
+const char* tcsfm_last_error(void);
+int tcsfm_abi_version(void);
+
+/* ---- inverse_warp2 (models/stn.py:234-273; pixel2cam :33-48, cam2pixel2 :198-231,
+ *      F.grid_sample bilinear/zeros/align_corners=False :266,271) ------------------
+ * out_img [B,3,H,W], out_valid / out_proj_depth / out_comp_depth [B,1,H,W]
+ * (any output pointer may be NULL to skip it). */
+int tcsfm_warp_fwd(const float* img, int64_t img_sb, int64_t img_sc,
+                   const float* depth, const float* ref_depth,
+                   const float* kinv, const float* proj,
+                   float* out_img, float* out_valid, float* out_proj_depth, float* out_comp_depth,
+                   int B, int H, int W, int flags, void* stream);
+
+/* Backward of the above (the autograd replay of stn.py:257-271).  g_out_* are the
+ * upstream gradients (NULL = zero).  g_depth is overwritten; g_ref_depth [B,1,H,W],
+ * g_proj [B,12] and the optional g_img [B,3,H,W] (contiguous) are accumulated
+ * (scatter / reduction).  NULL output pointers are skipped. */
+int tcsfm_warp_bwd(const float* img, int64_t img_sb, int64_t img_sc,
+                   const float* depth, const float* ref_depth,
+                   const float* kinv, const float* proj,
+                   const float* g_out_img, const float* g_out_proj_depth, const float* g_out_comp_depth,
+                   float* g_depth, float* g_ref_depth, float* g_proj, float* g_img,
+                   int B, int H, int W, int flags, void* stream);
+
+/* ---- SSIM_Loss.forward (losses.py:27-41) and its backward ---------------------
+ * x, y, out, g_out, g_x, g_y are contiguous [N,H,W] planes (N = B*C).
+ * g_x / g_y may be NULL. */
+int tcsfm_ssim_fwd(const float* x, const float* y, float* out,
+                   int N, int H, int W, int flags, void* stream);
+int tcsfm_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y,
+                   int N, int H, int W, int flags, void* stream);
+
+/* ---- Compute_Loss.compute_pairwise_loss (losses.py:151-183) fused with
+ *      mean_on_mask's sums (losses.py:142-149) --------------------------------------
+ * One launch evaluates n_groups independent pair groups (e.g. the 2*S
+ * direction/source combinations of Compute_Loss.forward, losses.py:99-127), each a
+ * batch of B pairs at HxW.  Host array of descriptors; all pointers inside are
+ * device pointers. */
+typedef struct tcsfm_pair_group {
+    const float* tgt_img;   int64_t tgt_sb, tgt_sc;   /* reconstruction target [B,3,H,W]  */
+    const float* ref_img;   int64_t ref_sb, ref_sc;   /* image that is sampled [B,3,H,W]  */
+    const float* tgt_depth;                           /* depth of the target   [B,1,H,W]  */
+    const float* ref_depth;                           /* depth that is sampled [B,1,H,W]  */
+    const float* kinv;                                /* [B,9]   */
+    const float* proj;                                /* [B,12]  */
+    /* forward outputs */
+    float* diff_img;        /* [B,1,H,W] per-pixel photometric error (losses.py:167,174); may be NULL */
+    float* mask;            /* [B,1,H,W] final valid_mask (auto*valid or valid, :158-162); required by bwd */
+    float* sums;            /* [4] accumulated: sum(diff*mask), sum(mask), sum(diff_depth*mask), 0 */
+    /* backward inputs */
+    const float* g_diff;    /* upstream grad of diff_img [B,1,H,W], may be NULL */
+    const float* g_scalars; /* device [2]: upstream grads of l_reprojection and l_depth, may be NULL */
+    /* backward outputs */
+    float* g_tgt_depth;     /* [B,1,H,W] overwritten */
+    float* g_ref_depth;     /* [B,1,H,W] accumulated; may be NULL when no depth term is active */
+    float* g_proj;          /* [B,12] accumulated */
+} tcsfm_pair_group;
+
+int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
+                        int B, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
+int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
+                        int B, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCSFM_H_ */

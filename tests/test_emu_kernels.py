@@ -1,0 +1,172 @@
+"""Kernel logic checked on the CPU through the test-only CUDA emulator build
+(tests/emu): same csrc/*.cu sources, same C ABI, host pointers.  Compared with the
+oracle and the reference-generated golden vectors using the CPU arithmetic
+flavour, so masks and forward values must match bit for bit."""
+import pytest
+import torch
+
+import goldens
+from emu_lib import emu
+from goldens import Golden, rel_l2
+from oracle import ref_torch as O
+from tcsfm_b200 import _cabi, _raw, stn, synth
+
+CPU = _cabi.ARITH_CPU
+
+
+def same(a, b):
+    return torch.equal(a.detach().float(), b.detach().float())
+
+
+def cfg_flags(cfg):
+    f = CPU | _cabi.SSIM
+    if cfg["with_auto_mask"]:
+        f |= _cabi.AUTO_MASK
+    if cfg["with_depth_mask"]:
+        f |= _cabi.DEPTH_MASK
+    if cfg["l_depth_consist"]:
+        f |= _cabi.DEPTH_CONSIST
+    return f
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+def test_warp_fwd_bwd_vs_golden(case):
+    g = Golden(case)
+    fr = g.frames()
+    pose = -fr["poses"][0]
+    kinv, proj = stn.projection_matrices(pose, fr["K"])
+    out_img, valid, pd, cd = _raw.warp_fwd(emu(), fr["sources"][0], fr["depths"][0], fr["depths"][1], kinv, proj, CPU)
+    assert same(valid, g.t("warp/valid_mask"))
+    assert same(cd, g.t("warp/computed_depth"))
+    assert rel_l2(out_img, g.t("warp/projected_img")) < 1e-6
+    assert rel_l2(pd, g.t("warp/projected_depth")) < 1e-6
+    # backward: grad wrt proj is mapped to the pose by autograd of the tiny algebra
+    p0 = pose.clone().requires_grad_(True)
+    _, proj_t = stn.projection_matrices(p0, fr["K"])
+    g_depth, g_ref, g_proj, g_src = _raw.warp_bwd(emu(), fr["sources"][0], fr["depths"][0], fr["depths"][1], kinv, proj,
+                                                  g.t("in/g_img"), g.t("in/g_pd"), g.t("in/g_cd"), CPU, need_img_grad=True)
+    proj_t.backward(g_proj)
+    assert rel_l2(g_depth, g.t("warp/g_depth")) < 2e-5
+    assert rel_l2(g_ref, g.t("warp/g_ref_depth")) < 2e-5
+    assert rel_l2(p0.grad, g.t("warp/g_pose")) < 2e-4
+    # grad wrt the sampled image against oracle autograd
+    src = fr["sources"][0].clone().requires_grad_(True)
+    pim, _, _, _ = O.inverse_warp2(src, fr["depths"][0], fr["depths"][1], pose, fr["K"])
+    (pim * g.t("in/g_img")).sum().backward()
+    assert rel_l2(g_src, src.grad) < 2e-5
+
+
+def test_warp_strided_channel_slice():
+    fr = synth.make_frames(2, 20, 70, seed=5)
+    six = torch.cat([fr["target"], fr["sources"][0]], 1)
+    pose = -fr["poses"][0]
+    kinv, proj = stn.projection_matrices(pose, fr["K"])
+    a = _raw.warp_fwd(emu(), six[:, 3:6], fr["depths"][0], fr["depths"][1], kinv, proj, CPU)
+    b = _raw.warp_fwd(emu(), fr["sources"][0], fr["depths"][0], fr["depths"][1], kinv, proj, CPU)
+    for x, y in zip(a, b):
+        assert same(x, y)
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+def test_ssim_vs_golden(case):
+    g = Golden(case)
+    x, y = g.t("in/target"), g.t("in/source0")
+    out = _raw.ssim_fwd(emu(), x, y, CPU)
+    assert same(out, g.t("ssim/map"))
+    g_x, g_y = _raw.ssim_bwd(emu(), x, y, g.t("in/g_img"), True, True, CPU)
+    assert rel_l2(g_x, g.t("ssim/g_x")) < 2e-5
+    assert rel_l2(g_y, g.t("ssim/g_y")) < 2e-5
+
+
+@pytest.mark.parametrize("hw", [(2, 2), (3, 5), (17, 65), (16, 64), (33, 130)])
+def test_ssim_odd_sizes_vs_oracle(hw):
+    h, w = hw
+    gen = torch.Generator().manual_seed(h * 100 + w)
+    x = torch.rand(2, 1, h, w, generator=gen).requires_grad_(True)
+    y = torch.rand(2, 1, h, w, generator=gen).requires_grad_(True)
+    gout = torch.randn(2, 1, h, w, generator=gen)
+    ref = O.ssim_dissimilarity(x, y)
+    (ref * gout).sum().backward()
+    out = _raw.ssim_fwd(emu(), x.detach(), y.detach(), CPU)
+    assert same(out, ref)
+    g_x, g_y = _raw.ssim_bwd(emu(), x.detach(), y.detach(), gout, True, True, CPU)
+    assert rel_l2(g_x, x.grad) < 2e-5 and rel_l2(g_y, y.grad) < 2e-5
+
+
+def run_pair(fr, cfg, g_diff, lrep_w=1.0, ldep_w=0.5):
+    pose = -fr["poses"][0]
+    p0 = pose.clone().requires_grad_(True)
+    kinv, proj = stn.projection_matrices(p0, fr["K"])
+    flags = cfg_flags(cfg)
+    batch = _raw.PairBatch([{"tgt_img": fr["target"], "ref_img": fr["sources"][0], "tgt_depth": fr["depths"][0],
+                             "ref_depth": fr["depths"][1], "kinv": kinv.detach(), "proj": proj.detach()}])
+    diff, mask, sums = _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, flags)
+    g_scalars = torch.tensor([[lrep_w, ldep_w if cfg["l_depth_consist"] else 0.0]])
+    need_ref = cfg["with_depth_mask"] or cfg["l_depth_consist"]
+    g_td, g_rd, g_proj = _raw.pair_loss_bwd(emu(), batch, mask, sums, g_diff.unsqueeze(0), g_scalars, 0.15, 0.85, flags, need_ref)
+    proj.backward(g_proj[0])
+    return diff[0], mask[0], sums[0], g_td[0], (g_rd[0] if need_ref else None), p0.grad
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+@pytest.mark.parametrize("tag", ["train", "full", "noauto"])
+def test_pair_loss_vs_golden(case, tag):
+    g = Golden(case)
+    fr = g.frames()
+    cfg = goldens.PAIR_CFGS[tag]
+    diff, mask, sums, g_td, g_rd, g_pose = run_pair(fr, cfg, g.t("in/g_diff"))
+    assert same(mask, g.t("pair_%s/valid_mask" % tag))
+    ref_diff = g.t("pair_%s/diff_img" % tag)
+    assert (diff - ref_diff).abs().max().item() < 2e-6
+    n_mask = float(mask.sum())
+    assert float(sums[1]) == n_mask
+    l_rep = float(sums[0] / sums[1]) if n_mask > 10000 else 0.0
+    assert abs(l_rep - float(g.t("pair_%s/l_reprojection" % tag))) <= 1e-5 * max(abs(l_rep), 1e-12)
+    if cfg["l_depth_consist"]:
+        l_dep = float(sums[2] / sums[1]) if n_mask > 10000 else 0.0
+        assert abs(l_dep - float(g.t("pair_%s/l_depth" % tag))) <= 1e-5 * max(abs(l_dep), 1e-12)
+    assert rel_l2(g_td, g.t("pair_%s/g_depth" % tag)) < 1e-4
+    if g_rd is not None:
+        assert rel_l2(g_rd, g.t("pair_%s/g_ref_depth" % tag)) < 1e-4
+    assert rel_l2(g_pose, g.t("pair_%s/g_pose" % tag)) < 1e-3
+
+
+def test_pair_loss_multi_group_and_partial_tiles():
+    """Two groups in one launch (forward + inverse direction) on a size that is not
+    a multiple of the 64x16 tile, against the oracle."""
+    fr = synth.make_frames(2, 37, 150, seed=9)
+    cfg = goldens.FULL_CFG
+    flags = cfg_flags(cfg)
+    K = fr["K"]
+    specs = [(fr["target"], fr["sources"][0], fr["depths"][0], fr["depths"][1], -fr["poses"][0]),
+             (fr["sources"][0], fr["target"], fr["depths"][1], fr["depths"][0], -fr["poses_inv"][0])]
+    groups = []
+    for tgt, ref, td, rd, pose in specs:
+        kinv, proj = stn.projection_matrices(pose, K)
+        groups.append({"tgt_img": tgt, "ref_img": ref, "tgt_depth": td, "ref_depth": rd, "kinv": kinv, "proj": proj})
+    batch = _raw.PairBatch(groups)
+    diff, mask, sums = _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, flags)
+    gen = torch.Generator().manual_seed(3)
+    g_diff = torch.randn(2, 2, 1, 37, 150, generator=gen)
+    g_td, g_rd, g_proj = _raw.pair_loss_bwd(emu(), batch, mask, sums, g_diff, None, 0.15, 0.85, flags, True)
+    for i, (tgt, ref, td, rd, pose) in enumerate(specs):
+        td_l, rd_l = td.clone().requires_grad_(True), rd.clone().requires_grad_(True)
+        _, _, rdiff, rmask, _ = O.pairwise_loss(cfg, tgt, ref, td_l, rd_l, pose, K)
+        assert same(mask[i], rmask)
+        assert (diff[i] - rdiff).abs().max().item() < 2e-6
+        (rdiff * g_diff[i]).sum().backward()
+        assert rel_l2(g_td[i], td_l.grad) < 1e-4
+        assert rel_l2(g_rd[i], rd_l.grad) < 1e-4
+
+
+def test_bad_arguments_report_errors():
+    fr = synth.make_frames(1, 8, 8, seed=0)
+    kinv, proj = stn.projection_matrices(-fr["poses"][0], fr["K"])
+    with pytest.raises(RuntimeError, match="bad shape"):
+        _raw.ssim_fwd(emu(), torch.rand(1, 1, 1, 8), torch.rand(1, 1, 1, 8))
+    batch = _raw.PairBatch([{"tgt_img": fr["target"], "ref_img": fr["sources"][0], "tgt_depth": fr["depths"][0],
+                             "ref_depth": None, "kinv": kinv, "proj": proj}])
+    with pytest.raises(RuntimeError, match="ref_depth"):
+        _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, CPU | _cabi.SSIM | _cabi.DEPTH_MASK)
+    with pytest.raises(RuntimeError, match="TCSFM_SSIM"):
+        _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, CPU)

@@ -1,0 +1,60 @@
+"""ctypes declarations of the C ABI in include/tcsfm.h (one place, used by the
+package loader and by the test-only emulator binding)."""
+import ctypes as C
+
+ABI_VERSION = 1
+
+ARITH_CPU = 1 << 0
+AUTO_MASK = 1 << 1
+SSIM = 1 << 2
+DEPTH_MASK = 1 << 3
+DEPTH_CONSIST = 1 << 4
+
+_fp = C.c_void_p          # device (or, in the emulator, host) pointer to float
+_i64 = C.c_int64
+
+
+class PairGroup(C.Structure):
+    """struct tcsfm_pair_group"""
+    _fields_ = [
+        ("tgt_img", _fp), ("tgt_sb", _i64), ("tgt_sc", _i64),
+        ("ref_img", _fp), ("ref_sb", _i64), ("ref_sc", _i64),
+        ("tgt_depth", _fp), ("ref_depth", _fp), ("kinv", _fp), ("proj", _fp),
+        ("diff_img", _fp), ("mask", _fp), ("sums", _fp),
+        ("g_diff", _fp), ("g_scalars", _fp),
+        ("g_tgt_depth", _fp), ("g_ref_depth", _fp), ("g_proj", _fp),
+    ]
+
+
+SIGNATURES = {
+    "tcsfm_last_error": (C.c_char_p, []),
+    "tcsfm_abi_version": (C.c_int, []),
+    "tcsfm_warp_fwd": (C.c_int, [_fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tcsfm_warp_bwd": (C.c_int, [_fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tcsfm_ssim_fwd": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tcsfm_ssim_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tcsfm_pair_loss_fwd": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "tcsfm_pair_loss_bwd": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_float, C.c_int, C.c_void_p]),
+}
+
+
+def bind(path):
+    """dlopen `path` and attach argtypes/restype for every declared symbol.
+    Raises if a symbol is missing or the ABI version differs."""
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.tcsfm_abi_version() != ABI_VERSION:
+        raise RuntimeError("%s: ABI version %d, expected %d" % (path, lib.tcsfm_abi_version(), ABI_VERSION))
+    return lib
+
+
+def check(lib, rc):
+    if rc != 0:
+        raise RuntimeError(lib.tcsfm_last_error().decode("utf-8", "replace") or "tcsfm call failed (%d)" % rc)

@@ -1,0 +1,166 @@
+"""Tensor-level marshalling onto the C ABI (include/tcsfm.h).
+
+These helpers take torch tensors, allocate the outputs with torch's allocator and
+pass raw pointers + the current CUDA stream to the library.  They are device
+agnostic on purpose (the test-only CUDA emulator drives the same code with host
+pointers); the public operators in ``ops.py`` are the ones that insist on CUDA.
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import PairGroup
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t):
+    if t.is_cuda:
+        return torch.cuda.current_stream(t.device).cuda_stream
+    return None
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def image_view(img, name="img"):
+    """(tensor, batch stride, channel stride) of a [B,C,H,W] fp32 view whose rows
+    are dense; other layouts (never produced by the reference's callers) are
+    copied once."""
+    if img.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, img.dtype))
+    b, c, h, w = img.shape
+    ok = img.stride(3) == 1 and img.stride(2) == w
+    if b > 1 and img.stride(0) < 0 or c > 1 and img.stride(1) < 0:
+        ok = False
+    if not ok:
+        img = img.contiguous()
+    return img, (img.stride(0) if b > 1 else c * h * w), (img.stride(1) if c > 1 else h * w)
+
+
+def warp_fwd(lib, img, depth, ref_depth, kinv, proj, flags=0, need_depths=True):
+    b, _, h, w = img.shape
+    img, sb, sc = image_view(img)
+    depth, ref_depth = _f32c(depth, "depth"), _f32c(ref_depth, "ref_depth")
+    kinv, proj = _f32c(kinv, "kinv"), _f32c(proj, "proj")
+    out_img = torch.empty((b, 3, h, w), dtype=torch.float32, device=img.device)
+    out_valid = torch.empty((b, 1, h, w), dtype=torch.float32, device=img.device)
+    out_pd = torch.empty_like(out_valid) if need_depths else None
+    out_cd = torch.empty_like(out_valid) if need_depths else None
+    rc = lib.tcsfm_warp_fwd(_ptr(img), sb, sc, _ptr(depth), _ptr(ref_depth), _ptr(kinv), _ptr(proj),
+                            _ptr(out_img), _ptr(out_valid), _ptr(out_pd), _ptr(out_cd),
+                            b, h, w, flags, _stream(img))
+    _cabi.check(lib, rc)
+    return out_img, out_valid, out_pd, out_cd
+
+
+def warp_bwd(lib, img, depth, ref_depth, kinv, proj, g_img, g_pd, g_cd, flags=0,
+             need_img_grad=False, need_ref_depth_grad=True):
+    b, _, h, w = img.shape
+    img, sb, sc = image_view(img)
+    depth, ref_depth = _f32c(depth, "depth"), _f32c(ref_depth, "ref_depth")
+    kinv, proj = _f32c(kinv, "kinv"), _f32c(proj, "proj")
+    g_img, g_pd, g_cd = _f32c(g_img, "g_img"), _f32c(g_pd, "g_pd"), _f32c(g_cd, "g_cd")
+    dev = img.device
+    g_depth = torch.empty((b, 1, h, w), dtype=torch.float32, device=dev)
+    g_ref = torch.empty((b, 1, h, w), dtype=torch.float32, device=dev) if need_ref_depth_grad else None
+    g_proj = torch.empty((b, 3, 4), dtype=torch.float32, device=dev)
+    g_src = torch.empty((b, 3, h, w), dtype=torch.float32, device=dev) if need_img_grad else None
+    rc = lib.tcsfm_warp_bwd(_ptr(img), sb, sc, _ptr(depth), _ptr(ref_depth), _ptr(kinv), _ptr(proj),
+                            _ptr(g_img), _ptr(g_pd), _ptr(g_cd),
+                            _ptr(g_depth), _ptr(g_ref), _ptr(g_proj), _ptr(g_src),
+                            b, h, w, flags, _stream(img))
+    _cabi.check(lib, rc)
+    return g_depth, g_ref, g_proj, g_src
+
+
+def ssim_fwd(lib, x, y, flags=0):
+    x, y = _f32c(x, "x"), _f32c(y, "y")
+    if x.shape != y.shape or x.dim() != 4:
+        raise ValueError("ssim: x and y must be [B,C,H,W] of equal shape")
+    b, c, h, w = x.shape
+    out = torch.empty_like(x)
+    _cabi.check(lib, lib.tcsfm_ssim_fwd(_ptr(x), _ptr(y), _ptr(out), b * c, h, w, flags, _stream(x)))
+    return out
+
+
+def ssim_bwd(lib, x, y, g_out, need_x=True, need_y=True, flags=0):
+    x, y, g_out = _f32c(x, "x"), _f32c(y, "y"), _f32c(g_out, "g_out")
+    b, c, h, w = x.shape
+    g_x = torch.empty_like(x) if need_x else None
+    g_y = torch.empty_like(x) if need_y else None
+    _cabi.check(lib, lib.tcsfm_ssim_bwd(_ptr(x), _ptr(y), _ptr(g_out), _ptr(g_x), _ptr(g_y),
+                                        b * c, h, w, flags, _stream(x)))
+    return g_x, g_y
+
+
+class PairBatch:
+    """Host-side descriptor array for one multi-group pair-loss launch; keeps every
+    tensor it points at alive."""
+
+    def __init__(self, groups):
+        # groups: list of dicts with tgt_img, ref_img, tgt_depth, ref_depth, kinv, proj
+        self.n = len(groups)
+        self.arr = (PairGroup * self.n)()
+        self.keep = []
+        first = groups[0]["tgt_img"]
+        self.b, _, self.h, self.w = first.shape
+        self.device = first.device
+        for i, g in enumerate(groups):
+            if g["tgt_img"].shape != first.shape or g["ref_img"].shape != first.shape:
+                raise ValueError("all pair groups of one launch must share [B,3,H,W]")
+            tgt, tsb, tsc = image_view(g["tgt_img"], "tgt_img")
+            ref, rsb, rsc = image_view(g["ref_img"], "ref_img")
+            td, rd = _f32c(g["tgt_depth"], "tgt_depth"), _f32c(g.get("ref_depth"), "ref_depth")
+            kinv, proj = _f32c(g["kinv"], "kinv"), _f32c(g["proj"], "proj")
+            self.keep.append((tgt, ref, td, rd, kinv, proj))
+            a = self.arr[i]
+            a.tgt_img, a.tgt_sb, a.tgt_sc = _ptr(tgt), tsb, tsc
+            a.ref_img, a.ref_sb, a.ref_sc = _ptr(ref), rsb, rsc
+            a.tgt_depth, a.ref_depth, a.kinv, a.proj = _ptr(td), _ptr(rd), _ptr(kinv), _ptr(proj)
+
+    def stream(self):
+        return _stream(self.keep[0][0])
+
+
+def pair_loss_fwd(lib, batch, w_l1, w_ssim, flags, want_diff=True):
+    """Returns (diff [G,B,1,H,W] or None, mask [G,B,1,H,W], sums [G,4])."""
+    g, b, h, w, dev = batch.n, batch.b, batch.h, batch.w, batch.device
+    diff = torch.empty((g, b, 1, h, w), dtype=torch.float32, device=dev) if want_diff else None
+    mask = torch.empty((g, b, 1, h, w), dtype=torch.float32, device=dev)
+    sums = torch.empty((g, 4), dtype=torch.float32, device=dev)
+    for i in range(g):
+        a = batch.arr[i]
+        a.diff_img = _ptr(diff[i]) if want_diff else None
+        a.mask = _ptr(mask[i])
+        a.sums = _ptr(sums[i])
+    _cabi.check(lib, lib.tcsfm_pair_loss_fwd(batch.arr, g, b, h, w, w_l1, w_ssim, flags, batch.stream()))
+    return diff, mask, sums
+
+
+def pair_loss_bwd(lib, batch, mask, sums, g_diff, g_scalars, w_l1, w_ssim, flags, need_ref_depth_grad):
+    """g_diff: [G,B,1,H,W] or None; g_scalars: [G,2] or None.
+    Returns (g_tgt_depth [G,B,1,H,W], g_ref_depth [G,B,1,H,W] or None, g_proj [G,B,3,4])."""
+    g, b, h, w, dev = batch.n, batch.b, batch.h, batch.w, batch.device
+    g_diff, g_scalars = _f32c(g_diff, "g_diff"), _f32c(g_scalars, "g_scalars")
+    g_td = torch.empty((g, b, 1, h, w), dtype=torch.float32, device=dev)
+    g_rd = torch.empty((g, b, 1, h, w), dtype=torch.float32, device=dev) if need_ref_depth_grad else None
+    g_proj = torch.empty((g, b, 3, 4), dtype=torch.float32, device=dev)
+    for i in range(g):
+        a = batch.arr[i]
+        a.mask, a.sums = _ptr(mask[i]), _ptr(sums[i])
+        a.g_diff = _ptr(g_diff[i]) if g_diff is not None else None
+        a.g_scalars = _ptr(g_scalars[i]) if g_scalars is not None else None
+        a.g_tgt_depth = _ptr(g_td[i])
+        a.g_ref_depth = _ptr(g_rd[i]) if need_ref_depth_grad else None
+        a.g_proj = _ptr(g_proj[i])
+    _cabi.check(lib, lib.tcsfm_pair_loss_bwd(batch.arr, g, b, h, w, w_l1, w_ssim, flags, batch.stream()))
+    return g_td, g_rd, g_proj

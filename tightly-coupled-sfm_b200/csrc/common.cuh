@@ -1,0 +1,67 @@
+// Shared launch / reduction helpers for the tcsfm sm_100a kernels.
+//
+// The same sources are also compiled by g++ against tests/emu/cuda_emu.h
+// (-DTCSFM_HOST_EMU) so that kernel logic can be checked without a GPU; that
+// build is test infrastructure only and is never loaded by the package.
+#pragma once
+
+#ifdef TCSFM_HOST_EMU
+#include "cuda_emu.h"
+#define TCSFM_SHARED static
+#define TCSFM_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem_base())
+#define TCSFM_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#define TCSFM_SHARED __shared__
+#define TCSFM_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; \
+    type* name = reinterpret_cast<type*>(name##_raw_)
+#define TCSFM_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
+
+#include "../../include/tcsfm.h"
+
+namespace tcsfm {
+
+// ---- error reporting (per-thread last error string, C ABI: tcsfm_last_error) ----
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// Block-wide sum of N per-thread partials -> one atomicAdd per value per block.
+// `red` is shared scratch of at least N * (threads/32) floats.  All threads of
+// the block must call this (it contains __syncthreads()).
+template <int N>
+__device__ __forceinline__ void block_atomic_accumulate(const float (&part)[N], float* red, float* dst,
+                                                        int tid, int nthreads) {
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        float s = warp_sum(part[i]);
+        if (lane == 0) red[i * nwarps + warp] = s;
+    }
+    __syncthreads();
+    if (tid < N) {
+        float s = 0.f;
+        for (int w = 0; w < nwarps; ++w) s += red[tid * nwarps + w];
+        if (s != 0.f) atomicAdd(dst + tid, s);
+    }
+    __syncthreads();
+}
+
+}  // namespace tcsfm

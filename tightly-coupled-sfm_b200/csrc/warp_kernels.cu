@@ -1,0 +1,138 @@
+// inverse_warp2 (reference models/stn.py:234-273) forward and backward.
+//
+// One thread per target pixel: back-project with K^-1 and the depth, apply
+// K[R|t], normalise, fill out-of-range coordinates with 2, bilinear-sample the
+// source image (3 ch) and source depth (1 ch).  The only HBM traffic is one
+// read of depth, the gathers (L1/L2 resident: neighbouring pixels hit the same
+// lines) and one write per output; no intermediate tensor is materialised.
+#include "tcsfm_math.cuh"
+
+namespace tcsfm {
+
+constexpr int kWarpThreads = 256;
+
+__global__ void __launch_bounds__(kWarpThreads)
+warp_fwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
+                const float* __restrict__ depth, const float* __restrict__ ref_depth,
+                const float* __restrict__ kinv, const float* __restrict__ proj,
+                float* __restrict__ out_img, float* __restrict__ out_valid,
+                float* __restrict__ out_pd, float* __restrict__ out_cd, Arith A) {
+    const int b = blockIdx.y;
+    const int n = A.H * A.W;
+    const int pix = blockIdx.x * kWarpThreads + threadIdx.x;
+    if (pix >= n) return;
+    const Cam c = load_cam(kinv, proj, b);
+    const int v = pix / A.W, u = pix - v * A.W;
+    const int64_t o = (int64_t)b * n + pix;
+    WarpPt p;
+    warp_point(c, A, u, v, __ldg(depth + o), p);
+    if (out_img) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+            out_img[((int64_t)b * 3 + ch) * n + pix] = sample_plane(img + b * img_sb + ch * img_sc, p, A.H, A.W);
+    }
+    if (out_valid) out_valid[o] = p.valid ? 1.f : 0.f;
+    if (out_pd) out_pd[o] = sample_plane(ref_depth + (int64_t)b * n, p, A.H, A.W);
+    if (out_cd) out_cd[o] = p.Z;
+}
+
+__device__ __forceinline__ void scatter_taps(float* __restrict__ plane, const WarpPt& p, float g, int H, int W) {
+    const bool x0in = (p.x0 >= 0) && (p.x0 < W), x1in = (p.x0 + 1 >= 0) && (p.x0 + 1 < W);
+    const bool y0in = (p.y0 >= 0) && (p.y0 < H), y1in = (p.y0 + 1 >= 0) && (p.y0 + 1 < H);
+    float* r0 = plane + (int64_t)p.y0 * W + p.x0;
+    if (y0in && x0in) atomicAdd(r0, g * (p.wx0 * p.wy0));
+    if (y0in && x1in) atomicAdd(r0 + 1, g * (p.wx1 * p.wy0));
+    if (y1in && x0in) atomicAdd(r0 + W, g * (p.wx0 * p.wy1));
+    if (y1in && x1in) atomicAdd(r0 + W + 1, g * (p.wx1 * p.wy1));
+}
+
+__global__ void __launch_bounds__(kWarpThreads)
+warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
+                const float* __restrict__ depth, const float* __restrict__ ref_depth,
+                const float* __restrict__ kinv, const float* __restrict__ proj,
+                const float* __restrict__ g_oimg, const float* __restrict__ g_opd, const float* __restrict__ g_ocd,
+                float* __restrict__ g_depth, float* __restrict__ g_ref_depth, float* __restrict__ g_proj,
+                float* __restrict__ g_img, Arith A) {
+    TCSFM_SHARED float red[12 * (kWarpThreads / 32)];
+    const int b = blockIdx.y;
+    const int n = A.H * A.W;
+    const int pix = blockIdx.x * kWarpThreads + threadIdx.x;
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+    if (pix < n) {
+        const Cam c = load_cam(kinv, proj, b);
+        const int v = pix / A.W, u = pix - v * A.W;
+        const int64_t o = (int64_t)b * n + pix;
+        WarpPt p;
+        warp_point(c, A, u, v, __ldg(depth + o), p);
+        float g_ix = 0.f, g_iy = 0.f;
+        if (g_oimg) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float g = __ldg(g_oimg + ((int64_t)b * 3 + ch) * n + pix);
+                const Taps t = gather_taps(img + b * img_sb + ch * img_sc, p, A.H, A.W);
+                bilinear_grad(t, p, g, g_ix, g_iy);
+                if (g_img) scatter_taps(g_img + ((int64_t)b * 3 + ch) * n, p, g, A.H, A.W);
+            }
+        }
+        if (g_opd) {
+            const float g = __ldg(g_opd + o);
+            const Taps t = gather_taps(ref_depth + (int64_t)b * n, p, A.H, A.W);
+            bilinear_grad(t, p, g, g_ix, g_iy);
+            if (g_ref_depth) scatter_taps(g_ref_depth + (int64_t)b * n, p, g, A.H, A.W);
+        }
+        const float g_Z = g_ocd ? __ldg(g_ocd + o) : 0.f;
+        const GeomGrad gg = geom_adjoint(c, A, p, g_ix, g_iy, g_Z);
+        if (g_depth) g_depth[o] = gg.g_depth;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            acc[i * 4 + 0] = gg.gp[i] * p.cam[0];
+            acc[i * 4 + 1] = gg.gp[i] * p.cam[1];
+            acc[i * 4 + 2] = gg.gp[i] * p.cam[2];
+            acc[i * 4 + 3] = gg.gp[i];
+        }
+    }
+    if (g_proj) block_atomic_accumulate<12>(acc, red, g_proj + b * 12, threadIdx.x, kWarpThreads);
+}
+
+}  // namespace tcsfm
+
+using namespace tcsfm;
+
+extern "C" int tcsfm_warp_fwd(const float* img, int64_t img_sb, int64_t img_sc,
+                              const float* depth, const float* ref_depth,
+                              const float* kinv, const float* proj,
+                              float* out_img, float* out_valid, float* out_proj_depth, float* out_comp_depth,
+                              int B, int H, int W, int flags, void* stream) {
+    if (B <= 0 || H < 2 || W < 2) { set_error("tcsfm_warp_fwd: bad shape B=%d H=%d W=%d", B, H, W); return 1; }
+    if (!img || !depth || !kinv || !proj || (out_proj_depth && !ref_depth)) {
+        set_error("tcsfm_warp_fwd: null input pointer"); return 1;
+    }
+    if (B > 65535) { set_error("tcsfm_warp_fwd: B=%d exceeds 65535", B); return 1; }
+    const Arith A = make_arith(H, W, flags);
+    dim3 grid((H * W + kWarpThreads - 1) / kWarpThreads, B), block(kWarpThreads);
+    TCSFM_LAUNCH(warp_fwd_kernel, grid, block, 0, stream, img, img_sb, img_sc, depth, ref_depth, kinv, proj,
+                 out_img, out_valid, out_proj_depth, out_comp_depth, A);
+    return check_launch("tcsfm_warp_fwd");
+}
+
+extern "C" int tcsfm_warp_bwd(const float* img, int64_t img_sb, int64_t img_sc,
+                              const float* depth, const float* ref_depth,
+                              const float* kinv, const float* proj,
+                              const float* g_out_img, const float* g_out_proj_depth, const float* g_out_comp_depth,
+                              float* g_depth, float* g_ref_depth, float* g_proj, float* g_img,
+                              int B, int H, int W, int flags, void* stream) {
+    if (B <= 0 || H < 2 || W < 2) { set_error("tcsfm_warp_bwd: bad shape B=%d H=%d W=%d", B, H, W); return 1; }
+    if (!img || !depth || !ref_depth || !kinv || !proj) { set_error("tcsfm_warp_bwd: null input pointer"); return 1; }
+    if (B > 65535) { set_error("tcsfm_warp_bwd: B=%d exceeds 65535", B); return 1; }
+    const Arith A = make_arith(H, W, flags);
+    const size_t plane = (size_t)B * H * W * sizeof(float);
+    if (g_ref_depth) cudaMemsetAsync(g_ref_depth, 0, plane, (cudaStream_t)stream);
+    if (g_proj) cudaMemsetAsync(g_proj, 0, (size_t)B * 12 * sizeof(float), (cudaStream_t)stream);
+    if (g_img) cudaMemsetAsync(g_img, 0, 3 * plane, (cudaStream_t)stream);
+    dim3 grid((H * W + kWarpThreads - 1) / kWarpThreads, B), block(kWarpThreads);
+    TCSFM_LAUNCH(warp_bwd_kernel, grid, block, 0, stream, img, img_sb, img_sc, depth, ref_depth, kinv, proj,
+                 g_out_img, g_out_proj_depth, g_out_comp_depth, g_depth, g_ref_depth, g_proj, g_img, A);
+    return check_launch("tcsfm_warp_bwd");
+}

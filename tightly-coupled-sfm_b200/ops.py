@@ -1,0 +1,116 @@
+"""Autograd operators over the CUDA C ABI (hand-written backward kernels).
+
+Every operator requires CUDA tensors and the built library; there is no CPU or
+eager-PyTorch fallback (a missing library or a CPU tensor raises).
+"""
+import torch
+
+from . import _cabi, _raw
+from ._lib import lib
+
+# Arithmetic flavour handed to the kernels: 0 reproduces eager PyTorch's CUDA
+# operators (the reference's production path); tests flip this to
+# _cabi.ARITH_CPU to compare bit-for-bit with CPU-generated golden vectors.
+ARITH_FLAGS = 0
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("tcsfm_b200 operators run on CUDA tensors only (got a %s tensor); "
+                               "there is no CPU fallback" % t.device.type)
+
+
+class InverseWarp2Fn(torch.autograd.Function):
+    """(img, depth, ref_depth, kinv, proj) -> (projected_img, valid_mask,
+    projected_depth, computed_depth); kernels: csrc/warp_kernels.cu."""
+
+    @staticmethod
+    def forward(ctx, img, depth, ref_depth, kinv, proj):
+        _require_cuda(img, depth, ref_depth, kinv, proj)
+        ctx.set_materialize_grads(False)
+        ctx.flags = ARITH_FLAGS
+        with torch.cuda.device(img.device):
+            out_img, valid, pd, cd = _raw.warp_fwd(lib(), img, depth, ref_depth, kinv, proj, ctx.flags)
+        ctx.save_for_backward(img, depth, ref_depth, kinv, proj)
+        ctx.mark_non_differentiable(valid)
+        return out_img, valid, pd, cd
+
+    @staticmethod
+    def backward(ctx, g_img, g_valid, g_pd, g_cd):
+        img, depth, ref_depth, kinv, proj = ctx.saved_tensors
+        need_img = ctx.needs_input_grad[0]
+        need_ref = ctx.needs_input_grad[2]
+        with torch.cuda.device(img.device):
+            g_depth, g_ref, g_proj, g_src = _raw.warp_bwd(
+                lib(), img, depth, ref_depth, kinv, proj, g_img, g_pd, g_cd, ctx.flags,
+                need_img_grad=need_img, need_ref_depth_grad=need_ref)
+        return g_src, g_depth, g_ref, None, g_proj
+
+
+class SsimFn(torch.autograd.Function):
+    """SSIM dissimilarity map of two [B,C,H,W] tensors; kernels: csrc/ssim_kernels.cu."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        _require_cuda(x, y)
+        with torch.cuda.device(x.device):
+            out = _raw.ssim_fwd(lib(), x, y, ARITH_FLAGS)
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, y = ctx.saved_tensors
+        with torch.cuda.device(x.device):
+            g_x, g_y = _raw.ssim_bwd(lib(), x, y, g_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ARITH_FLAGS)
+        return g_x, g_y
+
+
+class PairLossFn(torch.autograd.Function):
+    """G independent groups of B pairs in one launch (csrc/pair_kernels.cu).
+
+    apply(cfg, n_groups, *tensors) with tensors = for each group
+    (tgt_img, ref_img, tgt_depth, ref_depth, kinv, proj).  Returns
+    (diff [G,B,1,H,W], mask [G,B,1,H,W], l_reprojection [G], l_depth [G])."""
+
+    @staticmethod
+    def forward(ctx, cfg, n_groups, *tensors):
+        w_l1, w_ssim, flags = cfg
+        _require_cuda(*tensors)
+        groups = []
+        for i in range(n_groups):
+            t = tensors[6 * i:6 * i + 6]
+            groups.append({"tgt_img": t[0], "ref_img": t[1], "tgt_depth": t[2], "ref_depth": t[3],
+                           "kinv": t[4], "proj": t[5]})
+        flags = flags | ARITH_FLAGS
+        with torch.cuda.device(tensors[0].device):
+            batch = _raw.PairBatch(groups)
+            diff, mask, sums = _raw.pair_loss_fwd(lib(), batch, w_l1, w_ssim, flags)
+        # mean_on_mask (losses.py:142-149) without the host round trip
+        enough = sums[:, 1] > 10000
+        zero = torch.zeros_like(sums[:, 0])
+        l_rep = torch.where(enough, sums[:, 0] / sums[:, 1], zero)
+        l_dep = torch.where(enough, sums[:, 2] / sums[:, 1], zero)
+        ctx.batch, ctx.cfg, ctx.flags, ctx.n_groups = batch, (w_l1, w_ssim), flags, n_groups
+        ctx.save_for_backward(mask, sums)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(mask)
+        return diff, mask, l_rep, l_dep
+
+    @staticmethod
+    def backward(ctx, g_diff, g_mask, g_lrep, g_ldep):
+        mask, sums = ctx.saved_tensors
+        g_scalars = None
+        if g_lrep is not None or g_ldep is not None:
+            z = torch.zeros_like(sums[:, 0])
+            g_scalars = torch.stack([g_lrep if g_lrep is not None else z,
+                                     g_ldep if g_ldep is not None else z], dim=1)
+        need_ref = (ctx.flags & (_cabi.DEPTH_MASK | _cabi.DEPTH_CONSIST)) != 0
+        with torch.cuda.device(mask.device):
+            g_td, g_rd, g_proj = _raw.pair_loss_bwd(lib(), ctx.batch, mask, sums, g_diff, g_scalars,
+                                                    ctx.cfg[0], ctx.cfg[1], ctx.flags, need_ref)
+        grads = [None, None]
+        for i in range(ctx.n_groups):
+            grads += [None, None, g_td[i], g_rd[i] if need_ref else None, None, g_proj[i]]
+        return tuple(grads)
