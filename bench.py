@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Benchmark of the warp + SSIM/L1 photometric-loss hot path (BASELINE.json metric:
+"warp+SSIM/L1 loss fwd+bwd frames/s at 192x640").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload kitti|scannet]
+
+One *step* = one `Compute_Loss.forward` + `.backward()` over one synthetic minibatch
+(config 2 of BASELINE.json: B=8 KITTI-shaped 3-frame snippets at 192x640, forward and
+inverse direction for both sources = 32 pair evaluations, SSIM + L1 + auto-mask +
+depth-consistency mask/term, gradients to the three disparity maps and four poses).
+A *frame* is one target frame (2*S pair evaluations).
+
+Prints ONE JSON line (rank 0).  Multi-GPU (torchrun, one rank per GPU): every rank
+processes its own shard of minibatches, no data-path collective,
+`scaling: weak`; the timed region is bracketed by barrier + synchronize and the
+slowest rank's device time is used.
+
+`--impl reference` times the oracle port of the reference's PyTorch CPU path
+(oracle/ref_torch.py: the same ATen operators in the same order) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B, H, W, n_src, depth_range key, intrinsics)
+    "kitti": dict(b=8, h=192, w=640, n_src=2, desc="kitti_triplets_b8_192x640_fwd+inv_ssim_l1_automask_depthconsist"),
+    "scannet": dict(b=16, h=256, w=320, n_src=1, desc="scannet_pairs_b16_256x320_fwd+inv_ssim_l1_automask_depthconsist"),
+}
+LOSS_CFG = {"l1_weight": 0.15, "l_ssim_weight": 0.85, "l_smooth_weight": 0.05, "num_scales": 1,
+            "l_depth_consist_weight": 0.14, "min_depth": 0.06, "max_depth": 2.67, "l_smooth": False,
+            "l_reconstruction": True, "l_inverse": True, "l_depth_consist": True,
+            "with_auto_mask": True, "l_ssim": True, "with_depth_mask": True}
+METRIC = "warp+SSIM/L1 loss fwd+bwd frames/s at 192x640"
+N_INPUT_SETS = 8      # rotating input sets: 8 x ~47 MB > 126 MB of L2, so no step finds its inputs in L2
+
+
+def make_inputs(wl, seed, device, pin=False):
+    from tcsfm_b200 import synth
+    rng = synth.KITTI_DEPTH_RANGE if wl["h"] == 192 else synth.SCANNET_DEPTH_RANGE
+    base = synth.KITTI_K if wl["h"] == 192 else synth.SCANNET_K
+    fr = synth.make_frames(wl["b"], wl["h"], wl["w"], n_src=wl["n_src"], seed=seed, depth_range=rng,
+                           intrinsics=torch.tensor(base, dtype=torch.float32))
+    flat = {"target": fr["target"], "K": fr["K"]}
+    for j in range(wl["n_src"]):
+        flat["source%d" % j] = fr["sources"][j]
+        flat["pose%d" % j] = fr["poses"][j]
+        flat["pose_inv%d" % j] = fr["poses_inv"][j]
+    for j in range(1 + wl["n_src"]):
+        flat["disp%d" % j] = fr["disps"][j]
+    if pin:
+        return {k: v.pin_memory() for k, v in flat.items()}
+    return {k: v.to(device) for k, v in flat.items()}
+
+
+def run_step(loss_mod, inp, n_src, need_value=False):
+    disps = [inp["disp%d" % j].requires_grad_(True) for j in range(1 + n_src)]
+    poses = [inp["pose%d" % j].requires_grad_(True) for j in range(n_src)]
+    poses_inv = [inp["pose_inv%d" % j].requires_grad_(True) for j in range(n_src)]
+    for t in disps + poses + poses_inv:
+        t.grad = None
+    out = loss_mod([inp["source%d" % j] for j in range(n_src)], inp["target"], [poses, poses_inv],
+                   [[d] for d in disps], inp["K"])
+    total = out["total"].sum()
+    total.backward()
+    return total
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in o.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_throughput(wl, steps, warmup, threads):
+    """Times the oracle port of the reference's CPU path (fwd + bwd) on the host cores."""
+    from oracle import ref_torch as O
+    torch.set_num_threads(threads)
+    inp = make_inputs(wl, 0, "cpu")
+    n_src = wl["n_src"]
+
+    def step():
+        disps = [inp["disp%d" % j].clone().requires_grad_(True) for j in range(1 + n_src)]
+        poses = [inp["pose%d" % j].clone().requires_grad_(True) for j in range(n_src)]
+        poses_inv = [inp["pose_inv%d" % j].clone().requires_grad_(True) for j in range(n_src)]
+        out = O.compute_loss(LOSS_CFG, [inp["source%d" % j] for j in range(n_src)], inp["target"],
+                             [poses, poses_inv], [[d] for d in disps], inp["K"])
+        out["total"].sum().backward()
+        return float(out["total"].sum().detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return wl["b"] * steps / dt, dt / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-steps", type=int, default=None, help="steps of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    config = {"workload": wl["desc"], "batch_per_gpu": wl["b"], "pairs_per_step_per_gpu": 2 * wl["n_src"] * wl["b"],
+              "height": wl["h"], "width": wl["w"], "flags": "full (depth-consistency mask + term, auto-mask, SSIM+L1)",
+              "parallelism": "shard%d" % max(world, args.gpus),
+              "l2": "inputs rotate over %d sets (> L2 capacity)" % N_INPUT_SETS}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, args.cpu_steps or 6))
+        warm = max(1, min(args.warmup, 1))
+        fps, ms = cpu_port_throughput(wl, steps, warm, cores)
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                 "sample": "%d steps of the same B=%d minibatch, oracle port of the reference's "
+                                           "PyTorch CPU path, torch threads=%d" % (steps, wl["b"], cores)},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from tcsfm_b200 import _timing, losses
+    loss_mod = losses.Compute_Loss(LOSS_CFG)
+    n_src = wl["n_src"]
+    sets = [make_inputs(wl, 100 * rank + s, dev) for s in range(N_INPUT_SETS)]
+    host_sets = [make_inputs(wl, 100 * rank + s, dev, pin=True) for s in range(2)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    def step_resident(i):
+        run_step(loss_mod, sets[i % N_INPUT_SETS], n_src)
+
+    loss_holder = [0.0]
+
+    def step_e2e(i):
+        h = host_sets[i % 2]
+        inp = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+        loss_holder[0] = float(run_step(loss_mod, inp, n_src).detach())   # device -> host read of the loss
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _timing.LAUNCH_COUNT
+    ms_total = timed(step_resident, args.steps)
+    launches = _timing.LAUNCH_COUNT - launches0
+    clocks = sampler.summary() if sampler else None
+
+    # per-launch device time of the library calls, live over a second pass of the same steps
+    timer = _timing.KernelTimer()
+    with _timing.record(timer):
+        timed(step_resident, min(args.steps, 50))
+    ksum = timer.summary()
+
+    for i in range(min(args.warmup, 5)):
+        step_e2e(i)
+    e2e_steps = max(5, min(args.steps, 50))
+    ms_e2e = timed(step_e2e, e2e_steps)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    frames = wl["b"] * world
+    value = frames * args.steps / (ms_total / 1e3)
+    e2e_value = frames * e2e_steps / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+    npx = wl["h"] * wl["w"]
+    pairs = 2 * n_src * wl["b"]
+    # algorithmic bytes per pixel per pair (SURVEY.md §8d / DESIGN.md): fwd 32 R + 8 W, bwd 36 R + 8 W
+    bytes_per_launch = {"pair_loss_fwd": 40 * npx * pairs, "pair_loss_bwd": 44 * npx * pairs}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom = max((k for k in ksum if k in bytes_per_launch), key=lambda k: ksum[k]["avg_ms"], default=None)
+    roofline = None
+    if dom:
+        ach = bytes_per_launch[dom] / (ksum[dom]["avg_ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": ksum[dom]["avg_ms"],
+                    "algorithmic_bytes_per_launch": bytes_per_launch[dom],
+                    "step_algorithmic_GBps": 84 * npx * pairs / (ms_total / args.steps * 1e-3) / 1e9,
+                    "kernels": ksum}
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        csteps = args.cpu_steps or 4
+        cfps, cms = cpu_port_throughput(wl, csteps, 1, cores)
+        cpu_baseline = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port", "ms_per_step": cms,
+                        "sample": "%d steps of one B=%d minibatch of the same workload (oracle port of the "
+                                  "reference's PyTorch CPU path, torch threads=%d)" % (csteps, wl["b"], cores)}
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "pairs_per_s": value * 2 * n_src, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

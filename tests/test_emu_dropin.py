@@ -1,0 +1,122 @@
+"""Python-level wiring of the drop-ins (autograd functions, Compute_Loss
+orchestration) exercised on the CPU by pointing the operators at the test-only
+emulator build.  The package itself has no such path: ops.lib() loads only the
+CUDA library and the operators reject CPU tensors (see test_no_cpu_fallback)."""
+import pytest
+import torch
+
+import goldens
+from emu_lib import emu
+from goldens import Golden, rel_l2
+from tcsfm_b200 import _cabi, losses, ops, stn
+
+
+@pytest.fixture()
+def emu_ops(monkeypatch):
+    monkeypatch.setattr(ops, "lib", emu)
+    monkeypatch.setattr(ops, "_require_cuda", lambda *a: None)
+    monkeypatch.setattr(ops, "ARITH_FLAGS", _cabi.ARITH_CPU)
+
+
+def leaf(t):
+    return t.clone().detach().requires_grad_(True)
+
+
+def test_no_cpu_fallback():
+    x = torch.rand(1, 3, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        losses.SSIM_Loss()(x, x)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        stn.inverse_warp2(x, x[:, :1], x[:, :1], torch.zeros(1, 6), torch.eye(3).unsqueeze(0))
+
+
+def test_check_sizes_assertions(emu_ops):
+    x = torch.rand(1, 3, 8, 8)
+    with pytest.raises(AssertionError, match="wrong size for depth"):
+        stn.inverse_warp2(x, x, x[:, :1], torch.zeros(1, 6), torch.eye(3).unsqueeze(0))
+    with pytest.raises(AssertionError, match="wrong size for img"):
+        stn.inverse_warp2(x[:, :2], x[:, :1], x[:, :1], torch.zeros(1, 6), torch.eye(3).unsqueeze(0))
+    with pytest.raises(NotImplementedError):
+        stn.inverse_warp2(x, x[:, :1], x[:, :1], torch.zeros(1, 6), torch.eye(3).unsqueeze(0), 'border')
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+def test_inverse_warp2_autograd(emu_ops, case):
+    g = Golden(case)
+    fr = g.frames()
+    d0, d1, p0 = leaf(fr["depths"][0]), leaf(fr["depths"][1]), leaf(-fr["poses"][0])
+    pim, vm, pd, cd = stn.inverse_warp2(fr["sources"][0], d0, d1, p0, fr["K"], 'zeros')
+    assert torch.equal(vm, g.t("warp/valid_mask")) and not vm.requires_grad
+    ((pim * g.t("in/g_img")).sum() + (pd * g.t("in/g_pd")).sum() + (cd * g.t("in/g_cd")).sum()).backward()
+    assert rel_l2(d0.grad, g.t("warp/g_depth")) < 2e-5
+    assert rel_l2(d1.grad, g.t("warp/g_ref_depth")) < 2e-5
+    assert rel_l2(p0.grad, g.t("warp/g_pose")) < 2e-4
+
+
+def test_inverse_warp2_unused_outputs(emu_ops):
+    g = Golden(goldens.CASES[0])
+    fr = g.frames()
+    d0 = leaf(fr["depths"][0])
+    pim, _, _, _ = stn.inverse_warp2(fr["sources"][0], d0, fr["depths"][1], -fr["poses"][0], fr["K"])
+    pim.sum().backward()           # projected/computed depth grads are None inside backward
+    assert torch.isfinite(d0.grad).all()
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+def test_ssim_module(emu_ops, case):
+    g = Golden(case)
+    x, y = leaf(g.t("in/target")), leaf(g.t("in/source0"))
+    s = losses.SSIM_Loss()(x, y)
+    assert torch.equal(s, g.t("ssim/map"))
+    (s * g.t("in/g_img")).sum().backward()
+    assert rel_l2(x.grad, g.t("ssim/g_x")) < 2e-5 and rel_l2(y.grad, g.t("ssim/g_y")) < 2e-5
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+@pytest.mark.parametrize("tag", ["train", "full", "noauto"])
+def test_compute_pairwise_loss(emu_ops, case, tag):
+    g = Golden(case)
+    fr = g.frames()
+    mod = losses.Compute_Loss(goldens.PAIR_CFGS[tag])
+    d0, d1, p0 = leaf(fr["depths"][0]), leaf(fr["depths"][1]), leaf(-fr["poses"][0])
+    l_rep, l_dep, diff, vmask, none = mod.compute_pairwise_loss(fr["target"], fr["sources"][0], d0, d1, p0, fr["K"], 5)
+    assert none is None and diff.shape == vmask.shape == (fr["target"].shape[0], 1) + fr["target"].shape[2:]
+    assert torch.equal(vmask, g.t("pair_%s/valid_mask" % tag))
+    assert (diff - g.t("pair_%s/diff_img" % tag)).abs().max() < 2e-6
+    assert abs(float(l_rep) - float(g.t("pair_%s/l_reprojection" % tag))) <= 1e-5 * max(abs(float(l_rep)), 1e-12)
+    obj = l_rep + (diff * g.t("in/g_diff")).sum()
+    if torch.is_tensor(l_dep):
+        assert abs(float(l_dep) - float(g.t("pair_%s/l_depth" % tag))) <= 1e-5 * max(abs(float(l_dep)), 1e-12)
+        obj = obj + 0.5 * l_dep
+    else:
+        assert l_dep == 0
+    obj.backward()
+    assert rel_l2(d0.grad, g.t("pair_%s/g_depth" % tag)) < 1e-4
+    assert rel_l2(p0.grad, g.t("pair_%s/g_pose" % tag)) < 1e-3
+    if tag != "train":
+        assert rel_l2(d1.grad, g.t("pair_%s/g_ref_depth" % tag)) < 1e-4
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+@pytest.mark.parametrize("tag", ["train", "full", "smooth"])
+def test_compute_loss_forward_backward(emu_ops, case, tag):
+    g = Golden(case)
+    fr = g.frames()
+    mod = losses.Compute_Loss(goldens.LOSS_CFGS[tag])
+    disps = [leaf(d) for d in fr["disps"]]
+    poses, poses_inv = [leaf(p) for p in fr["poses"]], [leaf(p) for p in fr["poses_inv"]]
+    out = mod(fr["sources"], fr["target"], [poses, poses_inv], [[disps[0]], [disps[1]], [disps[2]]], fr["K"])
+    for k in ("l_reconstruct_inverse", "l_reconstruct_forward", "l_depth", "l_smooth", "total"):
+        assert out[k].shape == (1,), k
+        a, b = float(out[k]), float(g.t("loss_%s/%s" % (tag, k)))
+        assert abs(a - b) <= 1e-5 * max(abs(b), 1e-12), (k, a, b)
+    out["total"].sum().backward()
+    for j in range(3):
+        ref_g = g.t("loss_%s/g_disp%d" % (tag, j))
+        got = disps[j].grad if disps[j].grad is not None else torch.zeros_like(ref_g)
+        assert rel_l2(got, ref_g) < 1e-4, j
+    for j in range(2):
+        for name, lst in (("g_pose%d", poses), ("g_pose_inv%d", poses_inv)):
+            ref_g = g.t(("loss_%s/" % tag) + name % j)
+            got = lst[j].grad if lst[j].grad is not None else torch.zeros_like(ref_g)
+            assert rel_l2(got, ref_g) < 1e-3, (name, j)

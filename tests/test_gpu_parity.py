@@ -1,0 +1,238 @@
+"""Parity of the CUDA path (through the drop-in API -> ctypes -> C ABI ->
+sm_100a kernels) against the oracle and the reference-generated golden vectors.
+
+Tolerances (BASELINE.json north_star): loss <= 1e-5 relative, gradients <= 1e-4
+relative (rel-L2), validity masks bit-exact.  Two arbiters are used:
+  * golden fixtures / CPU oracle with the kernels' CPU arithmetic flavour;
+  * the oracle run with eager PyTorch on the same GPU (the reference's production
+    path) with the default CUDA flavour.
+Nothing here reads /root/reference."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+import goldens
+from goldens import Golden, rel_l2
+from oracle import ref_torch as O
+from tcsfm_b200 import _cabi, _lib, losses, ops, stn, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def leaf(t):
+    return t.clone().detach().requires_grad_(True)
+
+
+@pytest.fixture()
+def cpu_flavour(monkeypatch):
+    monkeypatch.setattr(ops, "ARITH_FLAGS", _cabi.ARITH_CPU)
+
+
+def test_native_library_is_loaded():
+    lib = _lib.lib()
+    assert lib.tcsfm_abi_version() == _cabi.ABI_VERSION
+    with open("/proc/self/maps") as f:
+        assert "libtcsfm_b200.so" in f.read()
+
+
+# ---------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("case", goldens.CASES)
+def test_warp_vs_golden(cpu_flavour, case):
+    g = Golden(case, DEV)
+    fr = g.frames()
+    d0, d1, p0 = leaf(fr["depths"][0]), leaf(fr["depths"][1]), leaf(-fr["poses"][0])
+    pim, vm, pd, cd = stn.inverse_warp2(fr["sources"][0], d0, d1, p0, fr["K"], 'zeros')
+    assert torch.equal(vm, g.t("warp/valid_mask"))
+    assert torch.equal(cd, g.t("warp/computed_depth"))
+    assert (pim - g.t("warp/projected_img")).abs().max() < 1e-6
+    assert (pd - g.t("warp/projected_depth")).abs().max() < 1e-6
+    ((pim * g.t("in/g_img")).sum() + (pd * g.t("in/g_pd")).sum() + (cd * g.t("in/g_cd")).sum()).backward()
+    assert rel_l2(d0.grad, g.t("warp/g_depth")) < 1e-4
+    assert rel_l2(d1.grad, g.t("warp/g_ref_depth")) < 1e-4
+    assert rel_l2(p0.grad, g.t("warp/g_pose")) < 1e-4
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+def test_ssim_vs_golden(cpu_flavour, case):
+    g = Golden(case, DEV)
+    x, y = leaf(g.t("in/target")), leaf(g.t("in/source0"))
+    s = losses.SSIM_Loss()(x, y)
+    assert (s - g.t("ssim/map")).abs().max() < 1e-6
+    (s * g.t("in/g_img")).sum().backward()
+    assert rel_l2(x.grad, g.t("ssim/g_x")) < 1e-4 and rel_l2(y.grad, g.t("ssim/g_y")) < 1e-4
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+@pytest.mark.parametrize("tag", ["train", "full", "noauto"])
+def test_pairwise_vs_golden(cpu_flavour, case, tag):
+    g = Golden(case, DEV)
+    fr = g.frames()
+    mod = losses.Compute_Loss(goldens.PAIR_CFGS[tag])
+    d0, d1, p0 = leaf(fr["depths"][0]), leaf(fr["depths"][1]), leaf(-fr["poses"][0])
+    l_rep, l_dep, diff, vmask, _ = mod.compute_pairwise_loss(fr["target"], fr["sources"][0], d0, d1, p0, fr["K"], 5)
+    assert torch.equal(vmask, g.t("pair_%s/valid_mask" % tag))
+    assert (diff - g.t("pair_%s/diff_img" % tag)).abs().max() < 1e-6
+    ref_l = float(g.t("pair_%s/l_reprojection" % tag))
+    assert abs(float(l_rep.detach()) - ref_l) <= 1e-5 * max(abs(ref_l), 1e-12)
+    obj = l_rep + (diff * g.t("in/g_diff")).sum()
+    if torch.is_tensor(l_dep):
+        ref_d = float(g.t("pair_%s/l_depth" % tag))
+        assert abs(float(l_dep.detach()) - ref_d) <= 1e-5 * max(abs(ref_d), 1e-12)
+        obj = obj + 0.5 * l_dep
+    obj.backward()
+    assert rel_l2(d0.grad, g.t("pair_%s/g_depth" % tag)) < 1e-4
+    assert rel_l2(p0.grad, g.t("pair_%s/g_pose" % tag)) < 1e-4
+    if tag != "train":
+        assert rel_l2(d1.grad, g.t("pair_%s/g_ref_depth" % tag)) < 1e-4
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+@pytest.mark.parametrize("tag", ["train", "full", "smooth"])
+def test_compute_loss_vs_golden(cpu_flavour, case, tag):
+    g = Golden(case, DEV)
+    fr = g.frames()
+    mod = losses.Compute_Loss(goldens.LOSS_CFGS[tag])
+    disps = [leaf(d) for d in fr["disps"]]
+    poses, poses_inv = [leaf(p) for p in fr["poses"]], [leaf(p) for p in fr["poses_inv"]]
+    out = mod(fr["sources"], fr["target"], [poses, poses_inv], [[disps[0]], [disps[1]], [disps[2]]], fr["K"])
+    for k in ("l_reconstruct_inverse", "l_reconstruct_forward", "l_depth", "l_smooth", "total"):
+        assert out[k].shape == (1,)
+        a, b = float(out[k].detach()), float(g.t("loss_%s/%s" % (tag, k)))
+        assert abs(a - b) <= 1e-5 * max(abs(b), 1e-12), (k, a, b)
+    out["total"].sum().backward()
+    for j in range(3):
+        ref_g = g.t("loss_%s/g_disp%d" % (tag, j))
+        got = disps[j].grad if disps[j].grad is not None else torch.zeros_like(ref_g)
+        assert rel_l2(got, ref_g) < 1e-4, j
+
+
+# ------------------------------------------------- same-device eager oracle, full sizes
+SHAPES = [(4, 192, 640, 0.01, synth.KITTI_DEPTH_RANGE), (4, 256, 320, 0.04, synth.SCANNET_DEPTH_RANGE),
+          (2, 256, 448, 0.02, synth.SCANNET_DEPTH_RANGE), (1, 376, 1242, 0.02, synth.KITTI_DEPTH_RANGE),
+          (3, 50, 77, 0.08, synth.KITTI_DEPTH_RANGE)]
+
+
+def frames(b, h, w, yaw, rng, seed=21):
+    return synth.make_frames(b, h, w, seed=seed, yaw=yaw, depth_range=rng, device=DEV,
+                             intrinsics=synth.scaled_intrinsics(h, w))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_warp_vs_eager_cuda(shape):
+    b, h, w, yaw, rng = shape
+    fr = frames(b, h, w, yaw, rng)
+    six = torch.cat([fr["target"], fr["sources"][0]], 1)           # callers pass imgs[:,3:6]
+    up = [torch.randn(b, c, h, w, device=DEV) for c in (3, 1, 1)]
+    res = []
+    for fn in (O.inverse_warp2, stn.inverse_warp2):
+        d0, d1, p0 = leaf(fr["depths"][0]), leaf(fr["depths"][1]), leaf(-fr["poses"][0])
+        pim, vm, pd, cd = fn(six[:, 3:6], d0, d1, p0, fr["K"], 'zeros')
+        ((pim * up[0]).sum() + (pd * up[1]).sum() + (cd * up[2]).sum()).backward()
+        res.append((pim, vm, pd, cd, d0.grad, d1.grad, p0.grad))
+    ref, got = res
+    assert torch.equal(got[1], ref[1]), "valid mask differs on %d px" % int((got[1] != ref[1]).sum())
+    assert torch.equal(got[3], ref[3])                               # computed depth, bit for bit
+    assert (got[0] - ref[0]).abs().max() < 1e-6 and (got[2] - ref[2]).abs().max() < 1e-6
+    assert rel_l2(got[4], ref[4]) < 1e-4
+    assert rel_l2(got[5], ref[5]) < 1e-4
+    assert rel_l2(got[6], ref[6]) < 1e-4
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("tag", ["train", "full"])
+def test_compute_loss_vs_eager_cuda(shape, tag):
+    b, h, w, yaw, rng = shape
+    fr = frames(b, h, w, yaw, rng)
+    cfg = dict(goldens.LOSS_CFGS[tag], min_depth=rng[0], max_depth=rng[1])
+    res = []
+    for impl in ("oracle", "cuda"):
+        disps = [leaf(d) for d in fr["disps"]]
+        poses, poses_inv = [leaf(p) for p in fr["poses"]], [leaf(p) for p in fr["poses_inv"]]
+        dl = [[disps[0]], [disps[1]], [disps[2]]]
+        if impl == "oracle":
+            out = O.compute_loss(cfg, fr["sources"], fr["target"], [poses, poses_inv], dl, fr["K"])
+        else:
+            out = losses.Compute_Loss(cfg)(fr["sources"], fr["target"], [poses, poses_inv], dl, fr["K"])
+        out["total"].sum().backward()
+        res.append((out, disps, poses, poses_inv))
+    (ro, rd, rp, rpi), (go, gd, gp, gpi) = res
+    for k in ("l_reconstruct_inverse", "l_reconstruct_forward", "l_depth", "total"):
+        a, bb = float(go[k].detach()), float(ro[k].detach())
+        assert abs(a - bb) <= 1e-5 * max(abs(bb), 1e-12), (k, a, bb)
+    for j in range(3):
+        assert rel_l2(gd[j].grad, rd[j].grad) < 1e-4, ("disp", j)
+    for j in range(2):
+        assert rel_l2(gp[j].grad, rp[j].grad) < 1e-4, ("pose", j)
+        assert rel_l2(gpi[j].grad, rpi[j].grad) < 1e-4, ("pose_inv", j)
+
+
+@pytest.mark.parametrize("shape", SHAPES[:3])
+def test_pair_masks_bit_exact_vs_eager_cuda(shape):
+    b, h, w, yaw, rng = shape
+    fr = frames(b, h, w, yaw, rng, seed=5)
+    for tag in ("train", "full", "noauto"):
+        cfg = goldens.PAIR_CFGS[tag]
+        for j in range(2):
+            args = (fr["target"], fr["sources"][j], fr["depths"][0], fr["depths"][1 + j], -fr["poses"][j], fr["K"])
+            ref = O.pairwise_loss(cfg, *args)
+            got = losses.Compute_Loss(cfg).compute_pairwise_loss(*args, 5)
+            assert torch.equal(got[3], ref[3]), (tag, j, int((got[3] != ref[3]).sum()))
+            assert (got[2] - ref[2]).abs().max() < 1e-6
+
+
+# ------------------------------------------------- size-independent properties, config-2 size
+def test_properties_full_size():
+    b, h, w = 8, 192, 640
+    fr = frames(b, h, w, 0.01, synth.KITTI_DEPTH_RANGE, seed=0)
+    cfg = goldens.FULL_CFG
+    mod = losses.Compute_Loss(cfg)
+    args = (fr["target"], fr["sources"][0], fr["depths"][0], fr["depths"][1], -fr["poses"][0], fr["K"])
+    l_rep, l_dep, diff, mask, _ = mod.compute_pairwise_loss(*args, 5)
+    # masks are 0/1, the reported means are the masked means of the returned maps
+    assert set(torch.unique(mask).tolist()) <= {0.0, 1.0}
+    assert mask.sum() > 10000
+    ref_mean = (diff.double() * mask.double()).sum() / mask.double().sum()
+    assert abs(float(l_rep) - float(ref_mean)) <= 1e-5 * float(ref_mean)
+    assert (diff >= 0).all() and (diff <= 1).all()
+    # determinism of the forward, linearity of the backward in the upstream gradient
+    l2, _, diff2, mask2, _ = mod.compute_pairwise_loss(*args, 5)
+    assert torch.equal(diff, diff2) and torch.equal(mask, mask2)
+    d0 = leaf(fr["depths"][0])
+    u, v = torch.randn_like(diff), torch.randn_like(diff)
+    outs = []
+    for up in (u, v, 2 * u - 3 * v):
+        d0.grad = None
+        _, _, dd, _, _ = mod.compute_pairwise_loss(fr["target"], fr["sources"][0], d0, fr["depths"][1], -fr["poses"][0], fr["K"], 5)
+        (dd * up).sum().backward()
+        outs.append(d0.grad.clone())
+    assert rel_l2(outs[2], 2 * outs[0] - 3 * outs[1]) < 1e-5
+    # fully out-of-view pose: empty mask -> the <=10000 rule returns exactly 0 and a zero gradient
+    far = fr["poses"][0].clone()
+    far[:, 0] = 1.0e4
+    d0.grad = None
+    l_far, _, _, m_far, _ = mod.compute_pairwise_loss(fr["target"], fr["sources"][0], d0, fr["depths"][1], far, fr["K"], 5)
+    assert float(m_far.sum()) == 0 and float(l_far) == 0
+    l_far.backward()
+    assert float(d0.grad.abs().max()) == 0
+
+
+def test_edge_cases_identity_and_clamped_depth():
+    b, h, w = 2, 64, 96
+    fr = frames(b, h, w, 0.0, synth.KITTI_DEPTH_RANGE, seed=3)
+    zero_pose = torch.zeros(b, 6, device=DEV)
+    a = O.inverse_warp2(fr["sources"][0], fr["depths"][0], fr["depths"][1], zero_pose, fr["K"])
+    g = stn.inverse_warp2(fr["sources"][0], fr["depths"][0], fr["depths"][1], zero_pose, fr["K"])
+    assert torch.equal(a[1], g[1]) and (a[0] - g[0]).abs().max() < 1e-6
+    # points behind the camera: Z is clamped to 1e-3 (models/stn.py:218) and gets no gradient
+    back = zero_pose.clone()
+    back[:, 2] = -10.0
+    d0r, d0g = leaf(fr["depths"][0]), leaf(fr["depths"][0])
+    a = O.inverse_warp2(fr["sources"][0], d0r, fr["depths"][1], back, fr["K"])
+    g = stn.inverse_warp2(fr["sources"][0], d0g, fr["depths"][1], back, fr["K"])
+    assert torch.equal(a[1], g[1]) and torch.equal(a[3], g[3]) and float(g[3].max()) == pytest.approx(1e-3)
+    a[3].sum().backward()
+    g[3].sum().backward()
+    assert torch.equal(d0r.grad, d0g.grad)

@@ -9,7 +9,7 @@ import ctypes as C
 
 import torch
 
-from . import _cabi
+from . import _cabi, _timing
 from ._cabi import PairGroup
 
 
@@ -55,10 +55,12 @@ def warp_fwd(lib, img, depth, ref_depth, kinv, proj, flags=0, need_depths=True):
     out_valid = torch.empty((b, 1, h, w), dtype=torch.float32, device=img.device)
     out_pd = torch.empty_like(out_valid) if need_depths else None
     out_cd = torch.empty_like(out_valid) if need_depths else None
-    rc = lib.tcsfm_warp_fwd(_ptr(img), sb, sc, _ptr(depth), _ptr(ref_depth), _ptr(kinv), _ptr(proj),
-                            _ptr(out_img), _ptr(out_valid), _ptr(out_pd), _ptr(out_cd),
-                            b, h, w, flags, _stream(img))
+    with _timing.launch("warp_fwd", img.is_cuda):
+        rc = lib.tcsfm_warp_fwd(_ptr(img), sb, sc, _ptr(depth), _ptr(ref_depth), _ptr(kinv), _ptr(proj),
+                                _ptr(out_img), _ptr(out_valid), _ptr(out_pd), _ptr(out_cd),
+                                b, h, w, flags, _stream(img))
     _cabi.check(lib, rc)
+    _timing.count_launch()
     return out_img, out_valid, out_pd, out_cd
 
 
@@ -74,11 +76,13 @@ def warp_bwd(lib, img, depth, ref_depth, kinv, proj, g_img, g_pd, g_cd, flags=0,
     g_ref = torch.empty((b, 1, h, w), dtype=torch.float32, device=dev) if need_ref_depth_grad else None
     g_proj = torch.empty((b, 3, 4), dtype=torch.float32, device=dev)
     g_src = torch.empty((b, 3, h, w), dtype=torch.float32, device=dev) if need_img_grad else None
-    rc = lib.tcsfm_warp_bwd(_ptr(img), sb, sc, _ptr(depth), _ptr(ref_depth), _ptr(kinv), _ptr(proj),
-                            _ptr(g_img), _ptr(g_pd), _ptr(g_cd),
-                            _ptr(g_depth), _ptr(g_ref), _ptr(g_proj), _ptr(g_src),
-                            b, h, w, flags, _stream(img))
+    with _timing.launch("warp_bwd", img.is_cuda):
+        rc = lib.tcsfm_warp_bwd(_ptr(img), sb, sc, _ptr(depth), _ptr(ref_depth), _ptr(kinv), _ptr(proj),
+                                _ptr(g_img), _ptr(g_pd), _ptr(g_cd),
+                                _ptr(g_depth), _ptr(g_ref), _ptr(g_proj), _ptr(g_src),
+                                b, h, w, flags, _stream(img))
     _cabi.check(lib, rc)
+    _timing.count_launch()
     return g_depth, g_ref, g_proj, g_src
 
 
@@ -88,7 +92,10 @@ def ssim_fwd(lib, x, y, flags=0):
         raise ValueError("ssim: x and y must be [B,C,H,W] of equal shape")
     b, c, h, w = x.shape
     out = torch.empty_like(x)
-    _cabi.check(lib, lib.tcsfm_ssim_fwd(_ptr(x), _ptr(y), _ptr(out), b * c, h, w, flags, _stream(x)))
+    with _timing.launch("ssim_fwd", x.is_cuda):
+        rc = lib.tcsfm_ssim_fwd(_ptr(x), _ptr(y), _ptr(out), b * c, h, w, flags, _stream(x))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
     return out
 
 
@@ -97,8 +104,10 @@ def ssim_bwd(lib, x, y, g_out, need_x=True, need_y=True, flags=0):
     b, c, h, w = x.shape
     g_x = torch.empty_like(x) if need_x else None
     g_y = torch.empty_like(x) if need_y else None
-    _cabi.check(lib, lib.tcsfm_ssim_bwd(_ptr(x), _ptr(y), _ptr(g_out), _ptr(g_x), _ptr(g_y),
-                                        b * c, h, w, flags, _stream(x)))
+    with _timing.launch("ssim_bwd", x.is_cuda):
+        rc = lib.tcsfm_ssim_bwd(_ptr(x), _ptr(y), _ptr(g_out), _ptr(g_x), _ptr(g_y), b * c, h, w, flags, _stream(x))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
     return g_x, g_y
 
 
@@ -142,7 +151,10 @@ def pair_loss_fwd(lib, batch, w_l1, w_ssim, flags, want_diff=True):
         a.diff_img = _ptr(diff[i]) if want_diff else None
         a.mask = _ptr(mask[i])
         a.sums = _ptr(sums[i])
-    _cabi.check(lib, lib.tcsfm_pair_loss_fwd(batch.arr, g, b, h, w, w_l1, w_ssim, flags, batch.stream()))
+    with _timing.launch("pair_loss_fwd", dev.type == "cuda"):
+        rc = lib.tcsfm_pair_loss_fwd(batch.arr, g, b, h, w, w_l1, w_ssim, flags, batch.stream())
+    _cabi.check(lib, rc)
+    _timing.count_launch()
     return diff, mask, sums
 
 
@@ -162,5 +174,8 @@ def pair_loss_bwd(lib, batch, mask, sums, g_diff, g_scalars, w_l1, w_ssim, flags
         a.g_tgt_depth = _ptr(g_td[i])
         a.g_ref_depth = _ptr(g_rd[i]) if need_ref_depth_grad else None
         a.g_proj = _ptr(g_proj[i])
-    _cabi.check(lib, lib.tcsfm_pair_loss_bwd(batch.arr, g, b, h, w, w_l1, w_ssim, flags, batch.stream()))
+    with _timing.launch("pair_loss_bwd", dev.type == "cuda"):
+        rc = lib.tcsfm_pair_loss_bwd(batch.arr, g, b, h, w, w_l1, w_ssim, flags, batch.stream())
+    _cabi.check(lib, rc)
+    _timing.count_launch()
     return g_td, g_rd, g_proj

@@ -1,0 +1,171 @@
+"""Drop-in for the reference's ``losses.py``: ``SSIM_Loss``, ``get_smooth_loss`` and
+``Compute_Loss`` with the reference's signatures and return structure, computed by
+the fused sm_100a kernels.
+
+``Compute_Loss.forward`` submits all 2*S direction/source pair evaluations of a
+scale (losses.py:99-127) as ONE forward launch and ONE backward launch; the
+mean-on-mask threshold (losses.py:144) is decided on the device, so the loss
+never synchronises with the host.
+"""
+import torch
+import torch.nn as nn
+
+from . import _cabi, ops
+from .stn import pose_vec2mat
+
+
+class SSIM_Loss(nn.Module):
+    """Layer to compute the SSIM dissimilarity between a pair of images
+    (reference losses.py:11-41): 3x3 mean/variance statistics on reflection-padded
+    inputs, clamp((1 - SSIM) / 2, 0, 1), C1 = 0.01**2, C2 = 0.03**2."""
+
+    def __init__(self):
+        super(SSIM_Loss, self).__init__()
+        self.C1 = 0.01 ** 2
+        self.C2 = 0.03 ** 2
+
+    def forward(self, x, y, valid_points=None):
+        return ops.SsimFn.apply(x, y)
+
+
+def disp_to_depth(disp, min_depth, max_depth):
+    """utils/learning_helpers.py:77-86."""
+    min_disp = 1 / max_depth
+    max_disp = 1 / min_depth
+    scaled_disp = min_disp + (max_disp - min_disp) * disp
+    depth = 1 / scaled_disp
+    return scaled_disp, depth
+
+
+def get_smooth_loss(disp, img):
+    """Edge-aware smoothness of the mean-normalised disparity (reference
+    losses.py:43-61).  Not yet fused: stock PyTorch operators."""
+    mean_disp = disp.mean(2, True).mean(3, True)
+    disp = disp / (mean_disp + 1e-7)
+    grad_disp_x = torch.abs(disp[:, :, :, :-1] - disp[:, :, :, 1:])
+    grad_disp_y = torch.abs(disp[:, :, :-1, :] - disp[:, :, 1:, :])
+    grad_img_x = torch.mean(torch.abs(img[:, :, :, :-1] - img[:, :, :, 1:]), 1, keepdim=True)
+    grad_img_y = torch.mean(torch.abs(img[:, :, :-1, :] - img[:, :, 1:, :]), 1, keepdim=True)
+    grad_disp_x = grad_disp_x * torch.exp(-grad_img_x)
+    grad_disp_y = grad_disp_y * torch.exp(-grad_img_y)
+    return grad_disp_x.mean() + grad_disp_y.mean()
+
+
+def _pair_flags(config):
+    flags = _cabi.SSIM
+    if config['with_auto_mask'] == True:    # noqa: E712 -- the reference compares with ==
+        flags |= _cabi.AUTO_MASK
+    if config['with_depth_mask']:
+        flags |= _cabi.DEPTH_MASK
+    if config['l_depth_consist'] == True:   # noqa: E712
+        flags |= _cabi.DEPTH_CONSIST
+    return flags
+
+
+class Compute_Loss(nn.modules.Module):
+    """Reference losses.py:64-194."""
+
+    def __init__(self, config):
+        super(Compute_Loss, self).__init__()
+        self.config = config
+        self.ssim = SSIM_Loss()
+        self.l1_weight = config['l1_weight']
+        self.l_ssim_weight = config['l_ssim_weight']
+        self.l_smooth_weight = config['l_smooth_weight']
+        self.num_scales = config['num_scales']
+        self.l_depth_consist_weight = config['l_depth_consist_weight']
+
+    # -- fused evaluation of a list of (tgt_img, ref_img, tgt_depth, ref_depth, pose) pairs
+    def _pair_groups(self, specs, intrinsics):
+        """One launch for all `specs`.  Returns per-group (l_reprojection, l_depth,
+        diff_img, valid_mask)."""
+        if intrinsics.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the intrinsics are not implemented")
+        if self.config['l_ssim'] != True:   # noqa: E712
+            raise NotImplementedError("the fused pair loss implements the l_ssim=True configuration "
+                                      "(the default of every reference script)")
+        n = len(specs)
+        kinv = intrinsics.inverse()                                  # models/stn.py:257
+        poses = torch.cat([s[4][:, 0:6] for s in specs], 0)          # [n*B, 6]
+        proj = intrinsics.repeat(n, 1, 1) @ pose_vec2mat(poses)      # models/stn.py:259-262
+        tensors = []
+        for tgt_img, ref_img, tgt_depth, ref_depth, _ in specs:
+            tensors += [tgt_img, ref_img, tgt_depth, ref_depth]
+        cfg = (float(self.config['l1_weight']), float(self.config['l_ssim_weight']), _pair_flags(self.config))
+        diff, mask, l_rep, l_dep = ops.PairLossFn.apply(cfg, n, kinv, proj, *tensors)
+        want_depth = self.config['l_depth_consist'] == True          # noqa: E712
+        return [(l_rep[i], l_dep[i] if want_depth else 0, diff[i], mask[i]) for i in range(n)]
+
+    def forward(self, source_imgs, target_img, poses, disparity, intrinsics, pose_vec_weight=None,
+                validate=False, epoch=5, target_img_right=None):
+        """Reference losses.py:75-140.  Returns the dict of [1]-shaped tensors
+        l_reconstruct_inverse, l_reconstruct_forward, l_depth, l_smooth, total."""
+        zero = torch.zeros(1).type_as(intrinsics)
+        losses = {'l_reconstruct_inverse': zero.clone(), 'l_reconstruct_forward': zero.clone(),
+                  'l_depth': zero.clone(), 'l_smooth': zero.clone()}
+        disparity, source_disparities = disparity[0], disparity[1:]
+        poses, poses_inv = poses[0], poses[1]
+        _, _, h, w = target_img.size()
+        cfg = self.config
+        for scale, disp in enumerate(disparity):
+            if scale != 0:
+                disp = nn.functional.interpolate(disp, (h, w), mode='nearest')
+            _, d = disp_to_depth(disp, cfg['min_depth'], cfg['max_depth'])
+            if cfg['l_smooth']:
+                losses['l_smooth'] += (self.l_smooth_weight * get_smooth_loss(disp, target_img)) / (2 ** scale)
+            if cfg['l_reconstruction']:
+                specs, roles = [], []
+                for j, source_img in enumerate(source_imgs):
+                    source_disparity = source_disparities[j][scale]
+                    if scale != 0:
+                        source_disparity = nn.functional.interpolate(source_disparity, (h, w), mode='nearest')
+                    _, source_d = disp_to_depth(source_disparity, cfg['min_depth'], cfg['max_depth'])
+                    if cfg['l_smooth']:
+                        losses['l_smooth'] += (self.l_smooth_weight * get_smooth_loss(source_disparity, source_img)) / (2 ** scale)
+                    if cfg['l_inverse']:   # inverse reconstruction: target reprojected into the source frame
+                        specs.append((source_img, target_img, source_d, d, -poses_inv[j]))
+                        roles.append('inv')
+                    specs.append((target_img, source_img, d, source_d, -poses[j]))
+                    roles.append('fwd')
+                results = self._pair_groups(specs, intrinsics)
+                reconstruction_errors = []
+                for role, (l_reprojection, l_depth, diff_img, _) in zip(roles, results):
+                    if cfg['l_depth_consist']:
+                        losses['l_depth'] += self.l_depth_consist_weight * l_depth
+                    if role == 'inv':
+                        losses['l_reconstruct_inverse'] += 0.3 * l_reprojection
+                    else:
+                        reconstruction_errors.append(diff_img)
+                reconstruction_errors = torch.cat(reconstruction_errors, 1)
+                reconstruction_errors, _ = torch.min(reconstruction_errors, 1)
+                losses['l_reconstruct_forward'] += reconstruction_errors.mean()
+        losses['total'] = 0
+        for key in ('l_reconstruct_inverse', 'l_reconstruct_forward', 'l_depth', 'l_smooth'):
+            losses[key] = losses[key] / (self.num_scales)
+            losses['total'] += losses[key]
+        return losses
+
+    def mean_on_mask(self, diff, valid_mask):
+        """Reference losses.py:142-149, decided on the device (no .item()): the masked
+        mean if more than 10000 mask entries are set, else a constant 0."""
+        mask = valid_mask.expand_as(diff)
+        total = mask.sum()
+        mean_value = (diff * mask).sum() / total.clamp(min=1)
+        return torch.where(total > 10000, mean_value, torch.zeros_like(mean_value))
+
+    def compute_pairwise_loss(self, tgt_img, ref_img, tgt_depth, ref_depth, pose, intrinsic, epoch, padding_mode='zeros'):
+        """Reference losses.py:151-183.  Returns (l_reprojection, l_depth, diff_img,
+        valid_mask, None)."""
+        if padding_mode != 'zeros':
+            raise NotImplementedError("only padding_mode='zeros' is implemented")
+        (l_reprojection, l_depth, diff_img, valid_mask), = self._pair_groups(
+            [(tgt_img, ref_img, tgt_depth, ref_depth, pose)], intrinsic)
+        return l_reprojection, l_depth, diff_img, valid_mask, None
+
+    def compute_reprojection_loss(self, pred, target):
+        """Reference losses.py:185-194 (no live caller)."""
+        diff_img = torch.abs(target - pred).mean(1, True)
+        if self.config['l_ssim'] == True:   # noqa: E712
+            ssim_loss = self.ssim(pred, target).mean(1, True)
+            diff_img = 0.85 * ssim_loss + 0.15 * diff_img
+        return diff_img

@@ -3,6 +3,8 @@
 Every operator requires CUDA tensors and the built library; there is no CPU or
 eager-PyTorch fallback (a missing library or a CPU tensor raises).
 """
+import contextlib
+
 import torch
 
 from . import _cabi, _raw
@@ -12,6 +14,12 @@ from ._lib import lib
 # operators (the reference's production path); tests flip this to
 # _cabi.ARITH_CPU to compare bit-for-bit with CPU-generated golden vectors.
 ARITH_FLAGS = 0
+
+
+def _guard(t):
+    """Makes the tensor's GPU current for the launch (the C ABI launches on the
+    current device / the stream it is handed)."""
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
 
 
 def _require_cuda(*tensors):
@@ -30,7 +38,7 @@ class InverseWarp2Fn(torch.autograd.Function):
         _require_cuda(img, depth, ref_depth, kinv, proj)
         ctx.set_materialize_grads(False)
         ctx.flags = ARITH_FLAGS
-        with torch.cuda.device(img.device):
+        with _guard(img):
             out_img, valid, pd, cd = _raw.warp_fwd(lib(), img, depth, ref_depth, kinv, proj, ctx.flags)
         ctx.save_for_backward(img, depth, ref_depth, kinv, proj)
         ctx.mark_non_differentiable(valid)
@@ -41,7 +49,7 @@ class InverseWarp2Fn(torch.autograd.Function):
         img, depth, ref_depth, kinv, proj = ctx.saved_tensors
         need_img = ctx.needs_input_grad[0]
         need_ref = ctx.needs_input_grad[2]
-        with torch.cuda.device(img.device):
+        with _guard(img):
             g_depth, g_ref, g_proj, g_src = _raw.warp_bwd(
                 lib(), img, depth, ref_depth, kinv, proj, g_img, g_pd, g_cd, ctx.flags,
                 need_img_grad=need_img, need_ref_depth_grad=need_ref)
@@ -54,7 +62,7 @@ class SsimFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y):
         _require_cuda(x, y)
-        with torch.cuda.device(x.device):
+        with _guard(x):
             out = _raw.ssim_fwd(lib(), x, y, ARITH_FLAGS)
         ctx.save_for_backward(x, y)
         return out
@@ -62,7 +70,7 @@ class SsimFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out):
         x, y = ctx.saved_tensors
-        with torch.cuda.device(x.device):
+        with _guard(x):
             g_x, g_y = _raw.ssim_bwd(lib(), x, y, g_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ARITH_FLAGS)
         return g_x, g_y
 
@@ -70,21 +78,23 @@ class SsimFn(torch.autograd.Function):
 class PairLossFn(torch.autograd.Function):
     """G independent groups of B pairs in one launch (csrc/pair_kernels.cu).
 
-    apply(cfg, n_groups, *tensors) with tensors = for each group
-    (tgt_img, ref_img, tgt_depth, ref_depth, kinv, proj).  Returns
+    apply(cfg, n_groups, kinv [B,3,3], proj [G*B,3,4], *tensors) with tensors = for
+    each group (tgt_img, ref_img, tgt_depth, ref_depth).  Returns
     (diff [G,B,1,H,W], mask [G,B,1,H,W], l_reprojection [G], l_depth [G])."""
 
     @staticmethod
-    def forward(ctx, cfg, n_groups, *tensors):
+    def forward(ctx, cfg, n_groups, kinv, proj, *tensors):
         w_l1, w_ssim, flags = cfg
-        _require_cuda(*tensors)
+        _require_cuda(kinv, proj, *tensors)
+        kinv, proj = kinv.contiguous(), proj.contiguous()
+        b = kinv.shape[0]
         groups = []
         for i in range(n_groups):
-            t = tensors[6 * i:6 * i + 6]
+            t = tensors[4 * i:4 * i + 4]
             groups.append({"tgt_img": t[0], "ref_img": t[1], "tgt_depth": t[2], "ref_depth": t[3],
-                           "kinv": t[4], "proj": t[5]})
+                           "kinv": kinv, "proj": proj[i * b:(i + 1) * b]})
         flags = flags | ARITH_FLAGS
-        with torch.cuda.device(tensors[0].device):
+        with _guard(kinv):
             batch = _raw.PairBatch(groups)
             diff, mask, sums = _raw.pair_loss_fwd(lib(), batch, w_l1, w_ssim, flags)
         # mean_on_mask (losses.py:142-149) without the host round trip
@@ -107,10 +117,10 @@ class PairLossFn(torch.autograd.Function):
             g_scalars = torch.stack([g_lrep if g_lrep is not None else z,
                                      g_ldep if g_ldep is not None else z], dim=1)
         need_ref = (ctx.flags & (_cabi.DEPTH_MASK | _cabi.DEPTH_CONSIST)) != 0
-        with torch.cuda.device(mask.device):
+        with _guard(mask):
             g_td, g_rd, g_proj = _raw.pair_loss_bwd(lib(), ctx.batch, mask, sums, g_diff, g_scalars,
                                                     ctx.cfg[0], ctx.cfg[1], ctx.flags, need_ref)
-        grads = [None, None]
+        grads = [None, None, None, g_proj.reshape(-1, 3, 4)]
         for i in range(ctx.n_groups):
-            grads += [None, None, g_td[i], g_rd[i] if need_ref else None, None, g_proj[i]]
+            grads += [None, None, g_td[i], g_rd[i] if need_ref else None]
         return tuple(grads)
