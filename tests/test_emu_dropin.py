@@ -120,3 +120,71 @@ def test_compute_loss_forward_backward(emu_ops, case, tag):
             ref_g = g.t(("loss_%s/" % tag) + name % j)
             got = lst[j].grad if lst[j].grad is not None else torch.zeros_like(ref_g)
             assert rel_l2(got, ref_g) < 1e-3, (name, j)
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+def test_pft_path(emu_ops, case):
+    """solve_pose_iteratively(return_errors=True) + compute_optimization_loss against
+    the reference-generated fixture (train_mono.py:41-120, optimizer.py:45-97)."""
+    from tcsfm_b200 import pft, synth, train_mono
+    g = Golden(case)
+    fr = g.frames()
+    seed = {"small_b2_24x40": 1, "mid_b2_64x96": 2, "yaw_b2_32x48": 3}[case]
+    net = synth.TinyPoseNet(seed=seed)
+    dl = [leaf(d) for d in fr["depths"]]
+    poses, poses_inv, outputs = train_mono.solve_pose_iteratively(3, dl, net, fr["target"], fr["sources"], fr["K"],
+                                                                  return_errors=True)
+    for side in ("fwd", "inv"):
+        for k in ("valid_mask", "auto_mask"):
+            assert torch.equal(outputs[side][k], g.t("pft/%s/%s" % (side, k))), (side, k)
+        for k in ("diff_img", "weight_mask", "auto_mask_error"):
+            assert (outputs[side][k] - g.t("pft/%s/%s" % (side, k))).abs().max() < 2e-6, (side, k)
+        assert outputs[side]["poses"].shape == (2 * fr["target"].shape[0], 3, 6)
+    for j in range(2):
+        assert (poses[j] - g.t("pft/pose%d" % j)).abs().max() < 1e-7
+        assert (poses_inv[j] - g.t("pft/pose_inv%d" % j)).abs().max() < 1e-7
+    tdisp = leaf(fr["disps"][0])
+    loss = pft.compute_optimization_loss(goldens.PFT_OPTIONS, fr["target"], tdisp, fr["disps"][0] * 0.9 + 0.02,
+                                         outputs["fwd"], outputs["inv"])
+    ref = float(g.t("pft/loss"))
+    assert abs(float(loss.detach()) - ref) <= 1e-5 * abs(ref)
+    loss.sum().backward()
+    # The depth-init term is SSIM on two smooth, 0.9-correlated disparity maps: variances of
+    # ~1e-5 come out of E[x^2] - mu^2 at ~0.3, so the reference's own fp32 gradient is ~6e-4
+    # (rel-L2) away from its fp64 evaluation (see test_ssim_gradient_noise_floor).
+    assert rel_l2(tdisp.grad, g.t("pft/g_tdisp")) < 5e-4
+    for j in range(3):
+        assert rel_l2(dl[j].grad, g.t("pft/g_depth%d" % j)) < 1e-4, j
+
+
+@pytest.mark.parametrize("case", goldens.CASES)
+def test_photometric_error(emu_ops, case):
+    from tcsfm_b200 import pft
+    g = Golden(case)
+    fr = g.frames()
+    with torch.no_grad():
+        res = pft.compute_photometric_error(fr["target"][:1], fr["sources"][0][:1], fr["depths"][0][:1],
+                                            fr["depths"][1][:1], fr["poses"][0][:1], fr["K"][:1])
+    assert torch.equal(res["valid_mask"], g.t("photo/valid_mask"))
+    for k in ("diff_img", "img_rec", "weight_mask"):
+        assert (res[k] - g.t("photo/%s" % k)).abs().max() < 2e-6, k
+
+
+def test_ssim_gradient_noise_floor(emu_ops):
+    """On smooth, highly correlated inputs (the disparity-init term, optimizer.py:89-90) the
+    kernel's gradient is closer to the reference's fp32 autograd than that is to fp64."""
+    from oracle import ref_torch as O
+    g = Golden("mid_b2_64x96")
+    x = g.frames()["disps"][0]
+    y = x * 0.9 + 0.02
+    gout = torch.full_like(x, 0.1 / x.numel())
+
+    def ref(dtype):
+        xx = x.to(dtype).clone().requires_grad_(True)
+        (O.ssim_dissimilarity(xx, y.to(dtype)) * gout.to(dtype)).sum().backward()
+        return xx.grad
+    r32, r64 = ref(torch.float32), ref(torch.float64)
+    xx = leaf(x)
+    (losses.SSIM_Loss()(xx, y) * gout).sum().backward()
+    assert rel_l2(xx.grad, r32) < rel_l2(r32, r64)
+    assert rel_l2(xx.grad, r64) < 1.5 * rel_l2(r32, r64)
