@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 1
+#define TCSFM_ABI_VERSION 3
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -45,6 +45,10 @@ extern "C" {
 #define TCSFM_SSIM             (1 << 2)   /* l_ssim           */
 #define TCSFM_DEPTH_MASK       (1 << 3)   /* with_depth_mask  */
 #define TCSFM_DEPTH_CONSIST    (1 << 4)   /* l_depth_consist  */
+/* backward only: several groups write into the same gradient buffers (e.g. the target
+ * depth is `tgt_depth` of the forward pairs and `ref_depth` of the inverse pairs).  All
+ * depth-gradient writes become atomic adds and the CALLER zeroes g_tgt_depth / g_ref_depth. */
+#define TCSFM_SHARED_GRADS     (1 << 5)
 
 const char* tcsfm_last_error(void);
 int tcsfm_abi_version(void);
@@ -95,19 +99,53 @@ typedef struct tcsfm_pair_group {
     float* diff_img;        /* [B,1,H,W] per-pixel photometric error (losses.py:167,174); may be NULL */
     float* mask;            /* [B,1,H,W] final valid_mask (auto*valid or valid, :158-162); required by bwd */
     float* sums;            /* [4] accumulated: sum(diff*mask), sum(mask), sum(diff_depth*mask), 0 */
+    float* coef;            /* [B,P,H,W] workspace, P = tcsfm_pair_coef_planes(): SSIM adjoint coefficients saved
+                               by the forward for the backward; NULL = inference only (no backward) */
     /* backward inputs */
     const float* g_diff;    /* upstream grad of diff_img [B,1,H,W], may be NULL */
     const float* g_scalars; /* device [2]: upstream grads of l_reprojection and l_depth, may be NULL */
+    /* per-pixel min over competing groups (losses.py:129-132): this group's diff_img is entry
+     * `min_index` of `min_count` maps spaced `min_stride` floats apart from `min_base`; the
+     * upstream gradient *g_min goes to the arg-min map (lowest index on ties).  NULL = unused. */
+    const float* min_base;  int64_t min_stride;  int32_t min_count, min_index;
+    const float* g_min;
     /* backward outputs */
     float* g_tgt_depth;     /* [B,1,H,W] overwritten */
     float* g_ref_depth;     /* [B,1,H,W] accumulated; may be NULL when no depth term is active */
     float* g_proj;          /* [B,12] accumulated */
 } tcsfm_pair_group;
 
+int tcsfm_pair_coef_planes(void);
 int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
                         int B, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
 int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
                         int B, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
+
+/* ---- glue of Compute_Loss.forward (losses.py:75-140) ----------------------------
+ * pose [N,6] (times `sign`; every call site passes -pose) -> K @ [Rx Ry Rz | t] as [N,12]
+ * (models/stn.py:81-116,143-158,262); row i uses K[i % Bk].  Bit-identical to the eager
+ * CUDA operators for N >= 2 (the batched k=3 SGEMM accumulation order).  The backward maps
+ * grad(K[R|t]) to the 6-DoF pose gradient. */
+int tcsfm_pose_proj_fwd(const float* pose, float sign, const float* K, int Bk, float* proj, int N, void* stream);
+int tcsfm_pose_proj_bwd(const float* pose, float sign, const float* K, int Bk, const float* g_proj,
+                        float* g_pose, int N, void* stream);
+
+/* out_sum[0] = sum_i min_j base[j*stride + i], j < count, i < n  (losses.py:129-131). */
+int tcsfm_min_reduce(const float* base, int64_t stride, int count, int64_t n, float* out_sum, void* stream);
+
+typedef struct tcsfm_frame_cfg {
+    int32_t n_groups;       /* pair groups of the launch, in the reference's evaluation order      */
+    int32_t role[8];        /* 0 = inverse reconstruction (scalar, x w_inverse), 1 = forward (min)  */
+    float   w_inverse;      /* 0.3, losses.py:116                                                   */
+    float   w_depth;        /* l_depth_consist_weight if l_depth_consist else 0, losses.py:114,121  */
+    int64_t n_min_pixels;   /* B*H*W: the mean of losses.py:132                                     */
+} tcsfm_frame_cfg;
+
+/* out[3] = (l_reconstruct_inverse, l_reconstruct_forward, l_depth) of one scale, from the pair
+ * kernels' sums [G,4] and the min-reduce sum (mean_on_mask's 10000-pixel rule on the device). */
+int tcsfm_frame_finalize(const float* sums, const float* min_sum, const tcsfm_frame_cfg* cfg, float* out, void* stream);
+/* g_out[3] -> g_scalars [G,2] and g_min [1], the upstream scalars tcsfm_pair_loss_bwd consumes. */
+int tcsfm_frame_bwd_prepare(const float* g_out, const tcsfm_frame_cfg* cfg, float* g_scalars, float* g_min, void* stream);
 
 #ifdef __cplusplus
 }

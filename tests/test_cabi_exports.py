@@ -35,5 +35,6 @@ def test_library_targets_sm_100a():
 
 def test_struct_layout_matches_header():
     import ctypes
-    # 3 pointers+2 strides each for the images, 15 further pointers: 6*8 + ... = 18 fields of 8 bytes
-    assert ctypes.sizeof(_cabi.PairGroup) == 18 * 8
+    # 2 x (pointer + 2 strides) for the images, 15 further pointers, a stride and two int32: 23 x 8 bytes
+    assert ctypes.sizeof(_cabi.PairGroup) == 23 * 8
+    assert ctypes.sizeof(_cabi.FrameCfg) == 4 + 32 + 4 + 4 + 4 + 8   # incl. 4 bytes of padding before the int64

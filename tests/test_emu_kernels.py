@@ -100,10 +100,10 @@ def run_pair(fr, cfg, g_diff, lrep_w=1.0, ldep_w=0.5):
     flags = cfg_flags(cfg)
     batch = _raw.PairBatch([{"tgt_img": fr["target"], "ref_img": fr["sources"][0], "tgt_depth": fr["depths"][0],
                              "ref_depth": fr["depths"][1], "kinv": kinv.detach(), "proj": proj.detach()}])
-    diff, mask, sums = _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, flags)
+    diff, mask, sums, coef = _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, flags)
     g_scalars = torch.tensor([[lrep_w, ldep_w if cfg["l_depth_consist"] else 0.0]])
     need_ref = cfg["with_depth_mask"] or cfg["l_depth_consist"]
-    g_td, g_rd, g_proj = _raw.pair_loss_bwd(emu(), batch, mask, sums, g_diff.unsqueeze(0), g_scalars, 0.15, 0.85, flags, need_ref)
+    g_td, g_rd, g_proj = _raw.pair_loss_bwd(emu(), batch, mask, sums, coef, g_diff.unsqueeze(0), g_scalars, 0.15, 0.85, flags, need_ref)
     proj.backward(g_proj[0])
     return diff[0], mask[0], sums[0], g_td[0], (g_rd[0] if need_ref else None), p0.grad
 
@@ -145,10 +145,10 @@ def test_pair_loss_multi_group_and_partial_tiles():
         kinv, proj = stn.projection_matrices(pose, K)
         groups.append({"tgt_img": tgt, "ref_img": ref, "tgt_depth": td, "ref_depth": rd, "kinv": kinv, "proj": proj})
     batch = _raw.PairBatch(groups)
-    diff, mask, sums = _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, flags)
+    diff, mask, sums, coef = _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, flags)
     gen = torch.Generator().manual_seed(3)
     g_diff = torch.randn(2, 2, 1, 37, 150, generator=gen)
-    g_td, g_rd, g_proj = _raw.pair_loss_bwd(emu(), batch, mask, sums, g_diff, None, 0.15, 0.85, flags, True)
+    g_td, g_rd, g_proj = _raw.pair_loss_bwd(emu(), batch, mask, sums, coef, g_diff, None, 0.15, 0.85, flags, True)
     for i, (tgt, ref, td, rd, pose) in enumerate(specs):
         td_l, rd_l = td.clone().requires_grad_(True), rd.clone().requires_grad_(True)
         _, _, rdiff, rmask, _ = O.pairwise_loss(cfg, tgt, ref, td_l, rd_l, pose, K)
@@ -170,3 +170,25 @@ def test_bad_arguments_report_errors():
         _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, CPU | _cabi.SSIM | _cabi.DEPTH_MASK)
     with pytest.raises(RuntimeError, match="TCSFM_SSIM"):
         _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, CPU)
+
+
+def test_pose_proj_fwd_bwd_vs_torch():
+    gen = torch.Generator().manual_seed(0)
+    pose = (0.2 * torch.randn(12, 6, generator=gen)).requires_grad_(True)
+    K = torch.tensor(synth.KITTI_K).repeat(4, 1, 1) + 0.01 * torch.rand(4, 3, 3, generator=gen)
+    ref = K.repeat(3, 1, 1) @ stn.pose_vec2mat(-pose)
+    got = _raw.pose_proj_fwd(emu(), pose.detach(), K, -1.0)
+    assert (got - ref).abs().max() < 1e-4 * ref.abs().max()
+    gp = torch.randn(12, 3, 4, generator=gen)
+    ref.backward(gp)
+    g_pose = _raw.pose_proj_bwd(emu(), pose.detach(), K, -1.0, gp)
+    assert rel_l2(g_pose, pose.grad) < 1e-5
+
+
+def test_min_reduce_and_routing_ties():
+    gen = torch.Generator().manual_seed(1)
+    stack = torch.rand(3, 2, 1, 9, 11, generator=gen)
+    stack[1] = torch.where(torch.rand(2, 1, 9, 11, generator=gen) < 0.3, stack[0], stack[1])   # exact ties
+    ref = torch.min(stack.permute(1, 0, 2, 3, 4).reshape(2, 3, 9, 11), 1)[0].sum()
+    got = _raw.min_reduce(emu(), stack[0], stack[0].numel(), 3, stack[0].numel())
+    assert abs(float(got) - float(ref)) < 1e-4

@@ -233,3 +233,22 @@ def test_edge_cases_identity_and_clamped_depth():
     a[3].sum().backward()
     g[3].sum().backward()
     assert torch.equal(d0r.grad, d0g.grad)
+
+
+def test_pose_proj_bit_exact_vs_eager_cuda():
+    """tcsfm_pose_proj_fwd reproduces `intrinsics @ pose_vec2mat(-pose)` (models/stn.py:259-262)
+    bit for bit on the same GPU (sinf/cosf of the CUDA math library, k-ascending FMA chains)."""
+    from tcsfm_b200 import _raw
+    gen = torch.Generator().manual_seed(0)
+    for n, bk in ((32, 8), (2, 2), (24, 6), (4096, 8)):
+        pose = (0.3 * torch.randn(n, 6, generator=gen)).to(DEV)
+        pose[0, 3:] = 0.0
+        K = (torch.tensor(synth.KITTI_K).repeat(bk, 1, 1) + 0.01 * torch.rand(bk, 3, 3, generator=gen)).to(DEV)
+        ref = K.repeat(n // bk, 1, 1) @ stn.pose_vec2mat(-pose)
+        got = _raw.pose_proj_fwd(_lib.lib(), pose, K, -1.0)
+        assert torch.equal(got, ref), (n, int((got != ref).sum()))
+        p = leaf(pose)
+        gp = torch.randn(n, 3, 4, device=DEV)
+        (K.repeat(n // bk, 1, 1) @ stn.pose_vec2mat(-p)).backward(gp)
+        g_pose = _raw.pose_proj_bwd(_lib.lib(), pose, K, -1.0, gp)
+        assert rel_l2(g_pose, p.grad) < 1e-5

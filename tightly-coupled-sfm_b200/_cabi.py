@@ -2,13 +2,14 @@
 package loader and by the test-only emulator binding)."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 3
 
 ARITH_CPU = 1 << 0
 AUTO_MASK = 1 << 1
 SSIM = 1 << 2
 DEPTH_MASK = 1 << 3
 DEPTH_CONSIST = 1 << 4
+SHARED_GRADS = 1 << 5
 
 _fp = C.c_void_p          # device (or, in the emulator, host) pointer to float
 _i64 = C.c_int64
@@ -20,10 +21,17 @@ class PairGroup(C.Structure):
         ("tgt_img", _fp), ("tgt_sb", _i64), ("tgt_sc", _i64),
         ("ref_img", _fp), ("ref_sb", _i64), ("ref_sc", _i64),
         ("tgt_depth", _fp), ("ref_depth", _fp), ("kinv", _fp), ("proj", _fp),
-        ("diff_img", _fp), ("mask", _fp), ("sums", _fp),
+        ("diff_img", _fp), ("mask", _fp), ("sums", _fp), ("coef", _fp),
         ("g_diff", _fp), ("g_scalars", _fp),
+        ("min_base", _fp), ("min_stride", _i64), ("min_count", C.c_int32), ("min_index", C.c_int32), ("g_min", _fp),
         ("g_tgt_depth", _fp), ("g_ref_depth", _fp), ("g_proj", _fp),
     ]
+
+
+class FrameCfg(C.Structure):
+    """struct tcsfm_frame_cfg"""
+    _fields_ = [("n_groups", C.c_int32), ("role", C.c_int32 * 8), ("w_inverse", C.c_float), ("w_depth", C.c_float),
+                ("n_min_pixels", _i64)]
 
 
 SIGNATURES = {
@@ -35,10 +43,16 @@ SIGNATURES = {
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tcsfm_ssim_fwd": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tcsfm_ssim_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tcsfm_pair_coef_planes": (C.c_int, []),
     "tcsfm_pair_loss_fwd": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "tcsfm_pair_loss_bwd": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "tcsfm_pose_proj_fwd": (C.c_int, [_fp, C.c_float, _fp, C.c_int, _fp, C.c_int, C.c_void_p]),
+    "tcsfm_pose_proj_bwd": (C.c_int, [_fp, C.c_float, _fp, C.c_int, _fp, _fp, C.c_int, C.c_void_p]),
+    "tcsfm_min_reduce": (C.c_int, [_fp, _i64, C.c_int, _i64, _fp, C.c_void_p]),
+    "tcsfm_frame_finalize": (C.c_int, [_fp, _fp, C.POINTER(FrameCfg), _fp, C.c_void_p]),
+    "tcsfm_frame_bwd_prepare": (C.c_int, [_fp, C.POINTER(FrameCfg), _fp, _fp, C.c_void_p]),
 }
 
 

@@ -5,7 +5,10 @@ import os
 from . import _cabi
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtcsfm_b200.so")
+# TCSFM_B200_LIB points at an alternative build of the same CUDA library (kernel tuning
+# experiments); it is still a CUDA build of csrc/ -- there is no non-CUDA implementation.
+LIB_PATH = os.environ.get("TCSFM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                             "libtcsfm_b200.so")
 
 
 def lib():

@@ -140,25 +140,27 @@ class PairBatch:
         return _stream(self.keep[0][0])
 
 
-def pair_loss_fwd(lib, batch, w_l1, w_ssim, flags, want_diff=True):
-    """Returns (diff [G,B,1,H,W] or None, mask [G,B,1,H,W], sums [G,4])."""
+def pair_loss_fwd(lib, batch, w_l1, w_ssim, flags, want_diff=True, want_grad=True):
+    """Returns (diff [G,B,1,H,W] or None, mask [G,B,1,H,W], sums [G,4], coef workspace or None)."""
     g, b, h, w, dev = batch.n, batch.b, batch.h, batch.w, batch.device
     diff = torch.empty((g, b, 1, h, w), dtype=torch.float32, device=dev) if want_diff else None
     mask = torch.empty((g, b, 1, h, w), dtype=torch.float32, device=dev)
     sums = torch.empty((g, 4), dtype=torch.float32, device=dev)
+    coef = torch.empty((g, b, lib.tcsfm_pair_coef_planes(), h, w), dtype=torch.float32, device=dev) if want_grad else None
     for i in range(g):
         a = batch.arr[i]
         a.diff_img = _ptr(diff[i]) if want_diff else None
         a.mask = _ptr(mask[i])
         a.sums = _ptr(sums[i])
+        a.coef = _ptr(coef[i]) if want_grad else None
     with _timing.launch("pair_loss_fwd", dev.type == "cuda"):
         rc = lib.tcsfm_pair_loss_fwd(batch.arr, g, b, h, w, w_l1, w_ssim, flags, batch.stream())
     _cabi.check(lib, rc)
     _timing.count_launch()
-    return diff, mask, sums
+    return diff, mask, sums, coef
 
 
-def pair_loss_bwd(lib, batch, mask, sums, g_diff, g_scalars, w_l1, w_ssim, flags, need_ref_depth_grad):
+def pair_loss_bwd(lib, batch, mask, sums, coef, g_diff, g_scalars, w_l1, w_ssim, flags, need_ref_depth_grad):
     """g_diff: [G,B,1,H,W] or None; g_scalars: [G,2] or None.
     Returns (g_tgt_depth [G,B,1,H,W], g_ref_depth [G,B,1,H,W] or None, g_proj [G,B,3,4])."""
     g, b, h, w, dev = batch.n, batch.b, batch.h, batch.w, batch.device
@@ -168,7 +170,7 @@ def pair_loss_bwd(lib, batch, mask, sums, g_diff, g_scalars, w_l1, w_ssim, flags
     g_proj = torch.empty((g, b, 3, 4), dtype=torch.float32, device=dev)
     for i in range(g):
         a = batch.arr[i]
-        a.mask, a.sums = _ptr(mask[i]), _ptr(sums[i])
+        a.mask, a.sums, a.coef = _ptr(mask[i]), _ptr(sums[i]), _ptr(coef[i])
         a.g_diff = _ptr(g_diff[i]) if g_diff is not None else None
         a.g_scalars = _ptr(g_scalars[i]) if g_scalars is not None else None
         a.g_tgt_depth = _ptr(g_td[i])
@@ -179,3 +181,98 @@ def pair_loss_bwd(lib, batch, mask, sums, g_diff, g_scalars, w_l1, w_ssim, flags
     _cabi.check(lib, rc)
     _timing.count_launch()
     return g_td, g_rd, g_proj
+
+
+# ---------------------------------------------------------------------------
+# glue kernels of Compute_Loss.forward (csrc/frame_kernels.cu)
+# ---------------------------------------------------------------------------
+
+def pose_proj_fwd(lib, pose, K, sign):
+    """pose [N,6], K [Bk,3,3] -> K @ [R|t] as [N,3,4] (row i uses K[i % Bk])."""
+    pose, K = _f32c(pose, "pose"), _f32c(K, "K")
+    n = pose.shape[0]
+    proj = torch.empty((n, 3, 4), dtype=torch.float32, device=pose.device)
+    with _timing.launch("pose_proj_fwd", pose.is_cuda):
+        rc = lib.tcsfm_pose_proj_fwd(_ptr(pose), sign, _ptr(K), K.shape[0], _ptr(proj), n, _stream(pose))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return proj
+
+
+def pose_proj_bwd(lib, pose, K, sign, g_proj):
+    pose, K, g_proj = _f32c(pose, "pose"), _f32c(K, "K"), _f32c(g_proj, "g_proj")
+    n = pose.shape[0]
+    g_pose = torch.empty((n, 6), dtype=torch.float32, device=pose.device)
+    with _timing.launch("pose_proj_bwd", pose.is_cuda):
+        rc = lib.tcsfm_pose_proj_bwd(_ptr(pose), sign, _ptr(K), K.shape[0], _ptr(g_proj), _ptr(g_pose), n, _stream(pose))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return g_pose
+
+
+def min_reduce(lib, first, stride, count, n):
+    """sum_i min_j first.flatten()[j*stride + i]; `first` is the first competing map."""
+    out = torch.empty((1,), dtype=torch.float32, device=first.device)
+    with _timing.launch("min_reduce", first.is_cuda):
+        rc = lib.tcsfm_min_reduce(_ptr(first), stride, count, n, _ptr(out), _stream(first))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return out
+
+
+def make_frame_cfg(roles, w_inverse, w_depth, n_min_pixels):
+    cfg = _cabi.FrameCfg()
+    cfg.n_groups = len(roles)
+    for i, r in enumerate(roles):
+        cfg.role[i] = r
+    cfg.w_inverse, cfg.w_depth, cfg.n_min_pixels = w_inverse, w_depth, n_min_pixels
+    return cfg
+
+
+def frame_finalize(lib, sums, min_sum, cfg):
+    out = torch.empty((3,), dtype=torch.float32, device=sums.device)
+    with _timing.launch("frame_finalize", sums.is_cuda):
+        rc = lib.tcsfm_frame_finalize(_ptr(sums), _ptr(min_sum), C.byref(cfg), _ptr(out), _stream(sums))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return out
+
+
+def frame_bwd_prepare(lib, g_out, cfg):
+    g_out = _f32c(g_out, "g_out")
+    g_scalars = torch.empty((cfg.n_groups, 2), dtype=torch.float32, device=g_out.device)
+    g_min = torch.empty((1,), dtype=torch.float32, device=g_out.device)
+    with _timing.launch("frame_bwd_prepare", g_out.is_cuda):
+        rc = lib.tcsfm_frame_bwd_prepare(_ptr(g_out), C.byref(cfg), _ptr(g_scalars), _ptr(g_min), _stream(g_out))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return g_scalars, g_min
+
+
+def pair_loss_bwd_shared(lib, batch, mask, sums, coef, g_scalars, g_min, min_info, g_depths, tgt_idx, ref_idx,
+                         w_l1, w_ssim, flags, need_ref_depth_grad):
+    """Backward of a multi-group launch whose groups share depth tensors: every group adds into
+    g_depths[tgt_idx[i]] / g_depths[ref_idx[i]] (zero-initialised here).  min_info =
+    (first diff map, stride, [group index -> position or -1], count).  Returns g_proj [G,B,3,4]."""
+    g, b, h, w, dev = batch.n, batch.b, batch.h, batch.w, batch.device
+    g_proj = torch.empty((g, b, 3, 4), dtype=torch.float32, device=dev)
+    g_depths.zero_()
+    min_first, min_stride, min_pos, min_count = min_info
+    for i in range(g):
+        a = batch.arr[i]
+        a.mask, a.sums, a.coef = _ptr(mask[i]), _ptr(sums[i]), _ptr(coef[i])
+        a.g_diff = None
+        a.g_scalars = _ptr(g_scalars[i])
+        a.g_tgt_depth = _ptr(g_depths[tgt_idx[i]])
+        a.g_ref_depth = _ptr(g_depths[ref_idx[i]]) if need_ref_depth_grad else None
+        a.g_proj = _ptr(g_proj[i])
+        if min_pos[i] >= 0:
+            a.min_base, a.min_stride, a.min_count, a.min_index = _ptr(min_first), min_stride, min_count, min_pos[i]
+            a.g_min = _ptr(g_min)
+        else:
+            a.min_base, a.g_min = None, None
+    with _timing.launch("pair_loss_bwd", dev.type == "cuda"):
+        rc = lib.tcsfm_pair_loss_bwd(batch.arr, g, b, h, w, w_l1, w_ssim, flags | _cabi.SHARED_GRADS, batch.stream())
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return g_proj

@@ -13,7 +13,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libtcsfm_b200.so")
-SOURCES = ["cabi.cu", "warp_kernels.cu", "ssim_kernels.cu", "pair_kernels.cu"]
+SOURCES = ["cabi.cu", "warp_kernels.cu", "ssim_kernels.cu", "pair_kernels.cu", "frame_kernels.cu"]
 HEADERS = ["common.cuh", "tcsfm_math.cuh", "tile.cuh", os.path.join("..", "..", "include", "tcsfm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               # parity-critical arithmetic uses explicit *_rn intrinsics (never contracted);
@@ -43,6 +43,17 @@ def is_current():
         return False
     with open(stamp) as f:
         return f.read().strip() == source_digest()
+
+
+def build_variant(out_path, defines):
+    """Tuning builds: same sources with extra -D macros, written to `out_path`."""
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D%s" % d for d in defines] + ["-I", CSRC, "-o", out_path] + \
+        [os.path.join(CSRC, s) for s in SOURCES]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("nvcc failed")
+    return proc.stderr
 
 
 def build(force=False, verbose=False):

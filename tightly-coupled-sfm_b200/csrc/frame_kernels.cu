@@ -1,0 +1,202 @@
+// Small kernels that replace the eager-PyTorch glue around the pair kernels inside
+// Compute_Loss.forward (reference losses.py:75-140) so that a whole loss step is a
+// dozen launches instead of ~200:
+//
+//   pose_proj_fwd/bwd   6-DoF pose -> K[R|t] (models/stn.py:81-116,143-158,262) and the
+//                       chain rule back from grad(K[R|t]) to the pose;
+//   min_reduce          sum over pixels of the per-pixel minimum over the source images'
+//                       error maps (losses.py:129-132);
+//   frame_finalize      mean_on_mask thresholds + the 0.3 / depth-consistency weights
+//                       (losses.py:112-127,142-149) from the pair kernels' sums;
+//   frame_bwd_prepare   the per-group upstream scalars the backward pair kernel consumes.
+#include "tcsfm_math.cuh"
+
+namespace tcsfm {
+
+// 3x3 @ 3xN product with the k-ascending FMA chain of the batched SGEMM (see dot3_blas).
+template <int N>
+__device__ __forceinline__ void matmul3(const float* a, const float* b, float* out) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            out[i * N + j] = dot3_blas(a[i * 3 + 0], a[i * 3 + 1], a[i * 3 + 2], b[0 * N + j], b[1 * N + j], b[2 * N + j]);
+}
+
+struct Euler {
+    float cx, sx, cy, sy, cz, sz;
+    float X[9], Y[9], Z[9];
+};
+
+__device__ __forceinline__ Euler euler_matrices(float rx, float ry, float rz) {
+    Euler e;
+    e.cx = cosf(rx); e.sx = sinf(rx);
+    e.cy = cosf(ry); e.sy = sinf(ry);
+    e.cz = cosf(rz); e.sz = sinf(rz);
+    const float zero = rz * 0.f;           // the reference builds its 0 / 1 entries from the angle tensor
+    const float one = zero + 1.f;
+    const float X[9] = {one, zero, zero, zero, e.cx, -e.sx, zero, e.sx, e.cx};
+    const float Y[9] = {e.cy, zero, e.sy, zero, one, zero, -e.sy, zero, e.cy};
+    const float Z[9] = {e.cz, -e.sz, zero, e.sz, e.cz, zero, zero, zero, one};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { e.X[i] = X[i]; e.Y[i] = Y[i]; e.Z[i] = Z[i]; }
+    return e;
+}
+
+__global__ void pose_proj_fwd_kernel(const float* __restrict__ pose, float sign, const float* __restrict__ K, int Bk,
+                                     float* __restrict__ proj, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float p[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) p[j] = sign * pose[i * 6 + j];
+    const Euler e = euler_matrices(p[3], p[4], p[5]);
+    float XY[9], R[9], T[12], P[12], Km[9];
+    matmul3<3>(e.X, e.Y, XY);
+    matmul3<3>(XY, e.Z, R);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        T[r * 4 + 0] = R[r * 3 + 0]; T[r * 4 + 1] = R[r * 3 + 1]; T[r * 4 + 2] = R[r * 3 + 2];
+        T[r * 4 + 3] = p[r];
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) Km[j] = K[(i % Bk) * 9 + j];
+    matmul3<4>(Km, T, P);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) proj[i * 12 + j] = P[j];
+}
+
+__global__ void pose_proj_bwd_kernel(const float* __restrict__ pose, float sign, const float* __restrict__ K, int Bk,
+                                     const float* __restrict__ g_proj, float* __restrict__ g_pose, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float p[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) p[j] = sign * pose[i * 6 + j];
+    const Euler e = euler_matrices(p[3], p[4], p[5]);
+    const float* Km = K + (i % Bk) * 9;
+    const float* gP = g_proj + i * 12;
+    // g_T = K^T g_P  (3x4)
+    float gT[12];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            gT[r * 4 + c] = Km[0 * 3 + r] * gP[0 * 4 + c] + Km[1 * 3 + r] * gP[1 * 4 + c] + Km[2 * 3 + r] * gP[2 * 4 + c];
+    float gR[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gR[r * 3 + c] = gT[r * 4 + c];
+    // R = X Y Z : g_X = g_R (YZ)^T, g_Y = X^T g_R Z^T, g_Z = (XY)^T g_R
+    float YZ[9], XY[9], gX[9], gY[9], gZ[9], tmp[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            YZ[r * 3 + c] = e.Y[r * 3 + 0] * e.Z[0 * 3 + c] + e.Y[r * 3 + 1] * e.Z[1 * 3 + c] + e.Y[r * 3 + 2] * e.Z[2 * 3 + c];
+            XY[r * 3 + c] = e.X[r * 3 + 0] * e.Y[0 * 3 + c] + e.X[r * 3 + 1] * e.Y[1 * 3 + c] + e.X[r * 3 + 2] * e.Y[2 * 3 + c];
+        }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            gX[r * 3 + c] = gR[r * 3 + 0] * YZ[c * 3 + 0] + gR[r * 3 + 1] * YZ[c * 3 + 1] + gR[r * 3 + 2] * YZ[c * 3 + 2];
+            gZ[r * 3 + c] = XY[0 * 3 + r] * gR[0 * 3 + c] + XY[1 * 3 + r] * gR[1 * 3 + c] + XY[2 * 3 + r] * gR[2 * 3 + c];
+            tmp[r * 3 + c] = e.X[0 * 3 + r] * gR[0 * 3 + c] + e.X[1 * 3 + r] * gR[1 * 3 + c] + e.X[2 * 3 + r] * gR[2 * 3 + c];
+        }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            gY[r * 3 + c] = tmp[r * 3 + 0] * e.Z[c * 3 + 0] + tmp[r * 3 + 1] * e.Z[c * 3 + 1] + tmp[r * 3 + 2] * e.Z[c * 3 + 2];
+    const float g_rx = -e.sx * gX[4] - e.cx * gX[5] + e.cx * gX[7] - e.sx * gX[8];
+    const float g_ry = -e.sy * gY[0] + e.cy * gY[2] - e.cy * gY[6] - e.sy * gY[8];
+    const float g_rz = -e.sz * gZ[0] - e.cz * gZ[1] + e.cz * gZ[3] - e.sz * gZ[4];
+    float* out = g_pose + i * 6;
+    out[0] = sign * gT[3]; out[1] = sign * gT[7]; out[2] = sign * gT[11];
+    out[3] = sign * g_rx; out[4] = sign * g_ry; out[5] = sign * g_rz;
+}
+
+constexpr int kReduceThreads = 256;
+
+__global__ void __launch_bounds__(kReduceThreads)
+min_reduce_kernel(const float* __restrict__ base, int64_t stride, int count, int64_t n, float* __restrict__ out) {
+    TCSFM_SHARED float red[kReduceThreads / 32];
+    float part[1] = {0.f};
+    for (int64_t i = (int64_t)blockIdx.x * kReduceThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kReduceThreads) {
+        float m = __ldg(base + i);
+        for (int j = 1; j < count; ++j) {
+            const float v = __ldg(base + j * stride + i);
+            m = (v < m || v != v) ? v : m;          // torch.min: lowest index on ties, NaN propagates
+        }
+        part[0] += m;
+    }
+    block_atomic_accumulate<1>(part, red, out, threadIdx.x, kReduceThreads);
+}
+
+__global__ void frame_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ min_sum, tcsfm_frame_cfg cfg,
+                                      float* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float l_inv = 0.f, l_dep = 0.f;
+    for (int g = 0; g < cfg.n_groups; ++g) {
+        const float s0 = sums[g * 4 + 0], s1 = sums[g * 4 + 1], s2 = sums[g * 4 + 2];
+        const bool enough = s1 > 10000.0f;                       // losses.py:144
+        const float l_rep = enough ? __fdiv_rn(s0, s1) : 0.f;
+        const float l_d = enough ? __fdiv_rn(s2, s1) : 0.f;
+        if (cfg.w_depth != 0.f) l_dep = __fadd_rn(l_dep, __fmul_rn(cfg.w_depth, l_d));          // :114-115,:121-122
+        if (cfg.role[g] == 0) l_inv = __fadd_rn(l_inv, __fmul_rn(cfg.w_inverse, l_rep));        // :116
+    }
+    out[0] = l_inv;
+    out[1] = min_sum ? __fdiv_rn(min_sum[0], (float)cfg.n_min_pixels) : 0.f;                    // :129-132
+    out[2] = l_dep;
+}
+
+__global__ void frame_bwd_prepare_kernel(const float* __restrict__ g_out, tcsfm_frame_cfg cfg,
+                                         float* __restrict__ g_scalars, float* __restrict__ g_min) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int g = 0; g < cfg.n_groups; ++g) {
+        g_scalars[g * 2 + 0] = (cfg.role[g] == 0) ? cfg.w_inverse * g_out[0] : 0.f;
+        g_scalars[g * 2 + 1] = cfg.w_depth * g_out[2];
+    }
+    g_min[0] = g_out[1] / (float)cfg.n_min_pixels;
+}
+
+}  // namespace tcsfm
+
+using namespace tcsfm;
+
+extern "C" int tcsfm_pose_proj_fwd(const float* pose, float sign, const float* K, int Bk, float* proj, int N, void* stream) {
+    if (!pose || !K || !proj || N <= 0 || Bk <= 0) { set_error("tcsfm_pose_proj_fwd: bad arguments"); return 1; }
+    TCSFM_LAUNCH(pose_proj_fwd_kernel, dim3((N + 63) / 64), dim3(64), 0, stream, pose, sign, K, Bk, proj, N);
+    return check_launch("tcsfm_pose_proj_fwd");
+}
+
+extern "C" int tcsfm_pose_proj_bwd(const float* pose, float sign, const float* K, int Bk, const float* g_proj,
+                                   float* g_pose, int N, void* stream) {
+    if (!pose || !K || !g_proj || !g_pose || N <= 0 || Bk <= 0) { set_error("tcsfm_pose_proj_bwd: bad arguments"); return 1; }
+    TCSFM_LAUNCH(pose_proj_bwd_kernel, dim3((N + 63) / 64), dim3(64), 0, stream, pose, sign, K, Bk, g_proj, g_pose, N);
+    return check_launch("tcsfm_pose_proj_bwd");
+}
+
+extern "C" int tcsfm_min_reduce(const float* base, int64_t stride, int count, int64_t n, float* out_sum, void* stream) {
+    if (!base || !out_sum || count <= 0 || n <= 0) { set_error("tcsfm_min_reduce: bad arguments"); return 1; }
+    cudaMemsetAsync(out_sum, 0, sizeof(float), (cudaStream_t)stream);
+    int64_t blocks = (n + kReduceThreads * 8 - 1) / (kReduceThreads * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    TCSFM_LAUNCH(min_reduce_kernel, dim3((unsigned)blocks), dim3(kReduceThreads), 0, stream, base, stride, count, n, out_sum);
+    return check_launch("tcsfm_min_reduce");
+}
+
+extern "C" int tcsfm_frame_finalize(const float* sums, const float* min_sum, const tcsfm_frame_cfg* cfg, float* out, void* stream) {
+    if (!sums || !cfg || !out || cfg->n_groups <= 0 || cfg->n_groups > 8) { set_error("tcsfm_frame_finalize: bad arguments"); return 1; }
+    TCSFM_LAUNCH(frame_finalize_kernel, dim3(1), dim3(32), 0, stream, sums, min_sum, *cfg, out);
+    return check_launch("tcsfm_frame_finalize");
+}
+
+extern "C" int tcsfm_frame_bwd_prepare(const float* g_out, const tcsfm_frame_cfg* cfg, float* g_scalars, float* g_min, void* stream) {
+    if (!g_out || !cfg || !g_scalars || !g_min || cfg->n_groups <= 0 || cfg->n_groups > 8) { set_error("tcsfm_frame_bwd_prepare: bad arguments"); return 1; }
+    TCSFM_LAUNCH(frame_bwd_prepare_kernel, dim3(1), dim3(32), 0, stream, g_out, *cfg, g_scalars, g_min);
+    return check_launch("tcsfm_frame_bwd_prepare");
+}

@@ -1,25 +1,38 @@
 // Fused pair loss: Compute_Loss.compute_pairwise_loss (reference losses.py:151-183)
 // + the sums of mean_on_mask (losses.py:142-149), forward and backward.
 //
-// Forward, per 64x16 tile of one pair: every thread back-projects / projects its
-// 4 pixels (and the CTA the 1-pixel halo ring), bilinear-gathers the source image
-// into a shared-memory tile next to the coalesced target tile, then evaluates
-// L1, the auto-mask, the 3x3 SSIM and the depth-consistency weight from shared
-// memory and block-reduces the three masked sums (one atomic each per CTA).
-// Nothing but diff_img / mask (4 B/px each) is written.
+// Both kernels are instruction-issue bound (hundreds of fp32 operations per pixel for
+// 40-44 algorithmic bytes), so the design minimises issued instructions while keeping
+// every rounding step of eager PyTorch:
 //
-// Backward recomputes the warped tile with a 2-pixel halo instead of saving it:
-// SSIM adjoint coefficients are built for the +1 ring channel by channel, each
-// own pixel gathers its 3x3 coefficient neighbourhood (reflection handled by tap
-// multiplicities), adds the L1 / depth-consistency adjoints and pushes the result
-// through the bilinear + projective adjoint: grad(target depth) is a direct
-// store, grad(source depth) a 4-tap atomic scatter, grad(K[R|t]) 12 block-reduced
-// accumulators per batch element.
+// Forward (64x16 tile, 256 threads, a vertical strip of 4 pixels per thread):
+//   A. each thread back-projects / projects its pixels (the CTA also the 1-pixel halo
+//      ring), gathers the 4 bilinear taps of the 3 source channels and stores
+//      (target, warped) as one float2 per cell of a shared-memory tile;
+//   C. per channel a thread slides a 3x3 register window down its strip: one LDS.64 per
+//      tap, squares/products once per tap, and the five avg_pool2d-ordered running sums
+//      as packed fp32x2 adds; /9 is an exact 3-instruction sequence.  L1, auto-mask,
+//      SSIM, depth-consistency weight, block-reduced masked sums (3 atomics per CTA).
+//   When a backward pass will follow, the SSIM adjoint coefficients (3 per channel) are
+//   written next to diff_img/mask (36 B/px of workspace) so that the backward neither
+//   re-warps a 2-pixel halo nor recomputes window statistics.
+//
+// Backward (same tiling): stage upstream-scaled coefficients of the +1 ring in shared
+// memory, gather each own pixel's 3x3 coefficient neighbourhood as separable rolling
+// sums (reflection = two conditional extra terms), add the L1 / depth-consistency
+// adjoints and push the result through the bilinear + projective adjoint: grad(target
+// depth) is a direct store, grad(source depth) a 4-tap atomic scatter, grad(K[R|t]) 12
+// block-reduced accumulators per batch element.
 #include "tile.cuh"
 
 namespace tcsfm {
 
+#ifndef TCSFM_PAIR_MIN_BLOCKS
+#define TCSFM_PAIR_MIN_BLOCKS 2      // resident CTAs per SM the register allocation targets
+#endif
+
 constexpr int kMaxGroups = 8;
+constexpr int kCoefPlanes = 10;      // 3 channels x (A, B, C) + the un-weighted photometric error
 
 struct PairLaunch {
     tcsfm_pair_group g[kMaxGroups];
@@ -33,24 +46,6 @@ struct PairCtx {
     int64_t tgt_sc, ref_sc;
 };
 
-// Fills one shared-memory cell of the target / warped tiles for an image pixel
-// (ry, rx) (already reflected).  Returns the geometry in `p`.
-__device__ __forceinline__ void fill_cell(const PairCtx& c, const Cam& cam, const Arith& A, int rx, int ry,
-                                          float* ts, float* ws, int cells, int cell, WarpPt& p) {
-    const int pix = ry * A.W + rx;
-    warp_point(cam, A, rx, ry, __ldg(c.tdep + pix), p);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        ws[ch * cells + cell] = sample_plane(c.ref + ch * c.ref_sc, p, A.H, A.W);
-        ts[ch * cells + cell] = __ldg(c.tgt + ch * c.tgt_sc + pix);
-    }
-}
-
-__device__ __forceinline__ void zero_cell(float* ts, float* ws, int cells, int cell) {
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) { ws[ch * cells + cell] = 0.f; ts[ch * cells + cell] = 0.f; }
-}
-
 __device__ __forceinline__ PairCtx make_ctx(const tcsfm_pair_group& g, int b, int n) {
     PairCtx c;
     c.tgt = g.tgt_img + b * g.tgt_sb;
@@ -62,12 +57,76 @@ __device__ __forceinline__ PairCtx make_ctx(const tcsfm_pair_group& g, int b, in
     return c;
 }
 
-__global__ void __launch_bounds__(kTileThreads)
+// Tap addressing shared by every plane sampled at one warped point.
+struct TapIdx {
+    int off;                       // y0 * W + x0 (may be out of range when a predicate is false)
+    bool nw, ne, sw, se;           // tap inside the image
+    float w_nw, w_ne, w_sw, w_se;  // bilinear weights, products rounded like ATen
+};
+
+__device__ __forceinline__ TapIdx make_taps(const WarpPt& p, int H, int W) {
+    TapIdx t;
+    const bool x0in = (p.x0 >= 0) && (p.x0 < W), x1in = (p.x0 >= -1) && (p.x0 < W - 1);
+    const bool y0in = (p.y0 >= 0) && (p.y0 < H), y1in = (p.y0 >= -1) && (p.y0 < H - 1);
+    t.off = p.y0 * W + p.x0;
+    t.nw = y0in && x0in; t.ne = y0in && x1in; t.sw = y1in && x0in; t.se = y1in && x1in;
+    t.w_nw = __fmul_rn(p.wx0, p.wy0);
+    t.w_ne = __fmul_rn(p.wx1, p.wy0);
+    t.w_sw = __fmul_rn(p.wx0, p.wy1);
+    t.w_se = __fmul_rn(p.wx1, p.wy1);
+    return t;
+}
+
+__device__ __forceinline__ Taps load_taps(const float* __restrict__ plane, const TapIdx& t, int W) {
+    Taps v;
+    const float* r0 = plane + t.off;
+    v.nw = t.nw ? __ldg(r0) : 0.f;
+    v.ne = t.ne ? __ldg(r0 + 1) : 0.f;
+    v.sw = t.sw ? __ldg(r0 + W) : 0.f;
+    v.se = t.se ? __ldg(r0 + W + 1) : 0.f;
+    return v;
+}
+
+// grid_sampler_2d bilinear accumulate: out = 0; out = fma(v, w, out) in nw, ne, sw, se order
+__device__ __forceinline__ float blend(const Taps& v, const TapIdx& t) {
+    float acc = __fmul_rn(v.nw, t.w_nw);
+    acc = __fmaf_rn(v.ne, t.w_ne, acc);
+    acc = __fmaf_rn(v.sw, t.w_sw, acc);
+    acc = __fmaf_rn(v.se, t.w_se, acc);
+    return acc;
+}
+
+// Fills one shared-memory cell with (target, warped source) of the image pixel (rx, ry).
+__device__ __forceinline__ void fill_cell(const PairCtx& c, const Cam& cam, const Arith& A, int rx, int ry,
+                                          float2* tw, int cells, int cell, WarpPt& p, TapIdx& ti) {
+    const int pix = ry * A.W + rx;
+    warp_point(cam, A, rx, ry, __ldg(c.tdep + pix), p);
+    ti = make_taps(p, A.H, A.W);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float w = blend(load_taps(c.ref + ch * c.ref_sc, ti, A.W), ti);
+        tw[ch * cells + cell] = make_float2(__ldg(c.tgt + ch * c.tgt_sc + pix), w);
+    }
+}
+
+__device__ __forceinline__ void zero_cell(float2* tw, int cells, int cell) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) tw[ch * cells + cell] = make_float2(0.f, 0.f);
+}
+
+// The halo ring of a Tile<1>, enumerated 0 .. 2*(kTileW+2) + 2*kTileH - 1.
+constexpr int kRingCells = 2 * (kTileW + 2) + 2 * kTileH;
+__device__ __forceinline__ void ring_cell(int r, int& cx, int& cy) {
+    if (r < kTileW + 2) { cx = r - 1; cy = -1; }
+    else if (r < 2 * (kTileW + 2)) { cx = r - (kTileW + 2) - 1; cy = kTileH; }
+    else if (r < 2 * (kTileW + 2) + kTileH) { cx = -1; cy = r - 2 * (kTileW + 2); }
+    else { cx = kTileW; cy = r - 2 * (kTileW + 2) - kTileH; }
+}
+
+__global__ void __launch_bounds__(kTileThreads, TCSFM_PAIR_MIN_BLOCKS)
 pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
     using T1 = Tile<1>;
-    TCSFM_DYN_SMEM(float, smem);
-    float* ts = smem;
-    float* ws = smem + 3 * T1::kCells;
+    TCSFM_DYN_SMEM(float2, tw);                       // [3][T1::kCells] (target, warped)
     TCSFM_SHARED float red[3 * (kTileThreads / 32)];
 
     const tcsfm_pair_group& g = L.g[blockIdx.z];
@@ -83,75 +142,106 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
     const bool depth_mask = (L.flags & TCSFM_DEPTH_MASK) != 0;
     const bool depth_consist = (L.flags & TCSFM_DEPTH_CONSIST) != 0;
     const bool need_depth = depth_mask || depth_consist;
+    const int tx = threadIdx.x & (kTileW - 1);
+    const int ty0 = (threadIdx.x >> 6) * kPixPerThread;
+    const int gx = x0 + tx;
 
     float own_mask[kPixPerThread], own_dd[kPixPerThread];
-    // ---- phase A: own pixels (geometry results kept in registers) ----
+    // ---- phase A: own pixels ----
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
-        int tx, ty;
-        own_pixel(threadIdx.x, k, tx, ty);
-        const int gx = x0 + tx, gy = y0 + ty;
-        const int cell = T1::cell(tx, ty);
+        const int gy = y0 + ty0 + k;
+        const int cell = T1::cell(tx, ty0 + k);
         float m = 0.f, dd = 0.f;
+        WarpPt p;
+        TapIdx ti;
         if (gx < W && gy < H) {
-            WarpPt p;
-            fill_cell(c, cam, A, gx, gy, ts, ws, T1::kCells, cell, p);
+            fill_cell(c, cam, A, gx, gy, tw, T1::kCells, cell, p, ti);
             m = p.valid ? 1.f : 0.f;
             if (auto_mask) {
                 const int pix = gy * W + gx;
                 float l1[3], ar[3];
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
-                    const float t = ts[ch * T1::kCells + cell];
-                    l1[ch] = clamp01_nan(fabsf(__fsub_rn(t, ws[ch * T1::kCells + cell])));
-                    ar[ch] = fabsf(__fsub_rn(t, __ldg(c.ref + ch * c.ref_sc + pix)));
+                    const float2 v = tw[ch * T1::kCells + cell];
+                    l1[ch] = clamp01_nan(fabsf(__fsub_rn(v.x, v.y)));
+                    ar[ch] = fabsf(__fsub_rn(v.x, __ldg(c.ref + ch * c.ref_sc + pix)));
                 }
                 if (!(mean3(l1[0], l1[1], l1[2], A) < mean3(ar[0], ar[1], ar[2], A))) m = 0.f;
             }
-            if (need_depth) dd = depth_inconsistency(p.Z, sample_plane(c.rdep, p, H, W));
+            if (need_depth) dd = depth_inconsistency(p.Z, blend(load_taps(c.rdep, ti, W), ti));
         } else {
             int ry, rx;
-            WarpPt p;
-            if (T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx)) fill_cell(c, cam, A, rx, ry, ts, ws, T1::kCells, cell, p);
-            else zero_cell(ts, ws, T1::kCells, cell);
+            if (T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx)) fill_cell(c, cam, A, rx, ry, tw, T1::kCells, cell, p, ti);
+            else zero_cell(tw, T1::kCells, cell);
         }
         own_mask[k] = m;
         own_dd[k] = dd;
     }
-    // ---- phase A': the halo ring ----
-    for (int cell = threadIdx.x; cell < T1::kCells; cell += kTileThreads) {
-        int cx, cy;
-        T1::cell_xy(cell, cx, cy);
-        if (cx >= 0 && cx < kTileW && cy >= 0 && cy < kTileH) continue;
-        int ry, rx;
+    // ---- phase A': the halo ring (one cell per thread) ----
+    if (threadIdx.x < kRingCells) {
+        int cx, cy, ry, rx;
+        ring_cell(threadIdx.x, cx, cy);
+        const int cell = T1::cell(cx, cy);
         WarpPt p;
-        if (T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx)) fill_cell(c, cam, A, rx, ry, ts, ws, T1::kCells, cell, p);
-        else zero_cell(ts, ws, T1::kCells, cell);
+        TapIdx ti;
+        if (T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx)) fill_cell(c, cam, A, rx, ry, tw, T1::kCells, cell, p, ti);
+        else zero_cell(tw, T1::kCells, cell);
     }
     __syncthreads();
-    // ---- phase C: photometric error per own pixel ----
+
+    // ---- phase C: 3x3 statistics down the strip, one channel at a time ----
+    float esum[kPixPerThread];
+    float* coef_base = g.coef ? g.coef + (int64_t)b * kCoefPlanes * n : nullptr;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float2* plane = tw + ch * T1::kCells;
+        float2 v[kPixPerThread + 2][3], sq[kPixPerThread + 2][3];
+        float ab[kPixPerThread + 2][3];
+#pragma unroll
+        for (int r = 0; r < kPixPerThread + 2; ++r) {
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                v[r][cc] = plane[T1::cell(tx - 1 + cc, ty0 - 1 + r)];
+                sq[r][cc] = square2_rn(v[r][cc]);
+                ab[r][cc] = __fmul_rn(v[r][cc].x, v[r][cc].y);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kPixPerThread; ++k) {
+            float2 wv[9], wsq[9];
+            float wab[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { wv[i] = v[k + i / 3][i % 3]; wsq[i] = sq[k + i / 3][i % 3]; wab[i] = ab[k + i / 3][i % 3]; }
+            const SsimStats s = ssim_stats_packed(wv, wsq, wab);
+            const SsimTerms t = ssim_terms(s, L.C1, L.C2);
+            const float2 ctr = v[k + 1][1];
+            const float l1 = clamp01_nan(fabsf(__fsub_rn(ctr.x, ctr.y)));
+            const float e = __fadd_rn(__fmul_rn(l1, L.w_l1), __fmul_rn(clamp01_nan(t.raw), L.w_ssim));
+            esum[k] = (ch == 0) ? e : __fadd_rn(esum[k], e);
+            const int gy = y0 + ty0 + k;
+            if (coef_base && gx < W && gy < H) {
+                // d diff / d ssim_c = (1 - dd) * (1/3) * w_ssim ; the backward multiplies by its upstream
+                const float gq = (depth_mask ? (1.0f - own_dd[k]) : 1.0f) * A.third * L.w_ssim;
+                const SsimCoef kf = ssim_coef(s, t, gq);            // x = target, y = warped
+                float* cp = coef_base + (int64_t)(3 * ch) * n + gy * W + gx;
+                cp[0] = kf.Ay; cp[n] = kf.B; cp[2 * (int64_t)n] = kf.Cc;
+            }
+        }
+    }
     float part[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
-        int tx, ty;
-        own_pixel(threadIdx.x, k, tx, ty);
-        const int gx = x0 + tx, gy = y0 + ty;
+        const int gy = y0 + ty0 + k;
         if (gx < W && gy < H) {
-            const int cell = T1::cell(tx, ty);
-            float e[3];
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const float* tc = ts + ch * T1::kCells + cell;
-                const float* wc = ws + ch * T1::kCells + cell;
-                const float l1 = clamp01_nan(fabsf(__fsub_rn(*tc, *wc)));
-                const float s = ssim_value(tc, wc, T1::kPitch, L.C1, L.C2);
-                e[ch] = __fadd_rn(__fmul_rn(l1, L.w_l1), __fmul_rn(s, L.w_ssim));
-            }
-            float diff = mean3(e[0], e[1], e[2], A);
-            if (depth_mask) diff = __fmul_rn(diff, __fsub_rn(1.0f, own_dd[k]));
+            const float s = esum[k];
+            const float diff0 = A.cpu_flavour ? div3_exact(s) : __fmul_rn(s, A.third);
+            float diff = diff0;
+            if (depth_mask) diff = __fmul_rn(diff0, __fsub_rn(1.0f, own_dd[k]));
             const int64_t o = (int64_t)b * n + gy * W + gx;
             if (g.diff_img) g.diff_img[o] = diff;
             if (g.mask) g.mask[o] = own_mask[k];
+            if (coef_base) coef_base[(int64_t)9 * n + gy * W + gx] = diff0;
             part[0] += diff * own_mask[k];
             part[1] += own_mask[k];
             if (depth_consist) part[2] += own_dd[k] * own_mask[k];
@@ -178,18 +268,32 @@ __device__ __forceinline__ BwdScalars bwd_scalars(const tcsfm_pair_group& g, boo
     return s;
 }
 
-__global__ void __launch_bounds__(kTileThreads)
+// Upstream gradient of diff_img at pixel `pix` of batch element b: the explicit per-pixel
+// gradient, the masked-mean term and the per-pixel min routing (losses.py:129-132).
+__device__ __forceinline__ float upstream_diff(const tcsfm_pair_group& g, const BwdScalars& sc, const float* gdiff,
+                                               const float* mask, int64_t bn, int pix, float m) {
+    float Gd = sc.c_rep * m;
+    if (gdiff) Gd += __ldg(gdiff + pix);
+    if (g.min_base) {
+        const float* mine = g.min_base + bn + pix;
+        const float v = __ldg(mine + (int64_t)g.min_index * g.min_stride);
+        bool win = true;
+        for (int j = 0; j < g.min_count; ++j) {
+            if (j == g.min_index) continue;
+            const float o = __ldg(mine + (int64_t)j * g.min_stride);
+            // torch.min(dim): the first index holding the minimum wins; a NaN is the minimum
+            if (j < g.min_index) win = win && !(o <= v || o != o);
+            else win = win && !(o < v || (o != o && v == v));
+        }
+        if (win) Gd += __ldg(g.g_min);
+    }
+    return Gd;
+}
+
+__global__ void __launch_bounds__(kTileThreads, TCSFM_PAIR_MIN_BLOCKS)
 pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
-    using T2 = Tile<2>;
     using T1 = Tile<1>;
-    TCSFM_DYN_SMEM(float, smem);
-    float* ts = smem;                          // [3][T2]
-    float* ws = ts + 3 * T2::kCells;           // [3][T2]
-    float* G1 = ws + 3 * T2::kCells;           // [T1] upstream grad of each channel's ssim value at q
-    float* cA = G1 + T1::kCells;               // [T1] coefficients of the current channel
-    float* cB = cA + T1::kCells;
-    float* cC = cB + T1::kCells;
-    float* sv = cC + T1::kCells;               // [T1] ssim value of the current channel (depth-mask only)
+    TCSFM_DYN_SMEM(float, cs);                     // [9][T1::kCells] upstream-scaled coefficients
     TCSFM_SHARED float red[12 * (kTileThreads / 32)];
 
     const tcsfm_pair_group& g = L.g[blockIdx.z];
@@ -204,88 +308,63 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     const bool depth_mask = (L.flags & TCSFM_DEPTH_MASK) != 0;
     const bool depth_consist = (L.flags & TCSFM_DEPTH_CONSIST) != 0;
     const bool need_depth = depth_mask || depth_consist;
+    const bool shared_grads = (L.flags & TCSFM_SHARED_GRADS) != 0;
     const BwdScalars sc = bwd_scalars(g, depth_consist);
     const float* gdiff = g.g_diff ? g.g_diff + (int64_t)b * n : nullptr;
     const float* mask = g.mask + (int64_t)b * n;
+    const float* coef = g.coef + (int64_t)b * kCoefPlanes * n;
+    const int tx = threadIdx.x & (kTileW - 1);
+    const int ty0 = (threadIdx.x >> 6) * kPixPerThread;
+    const int gx = x0 + tx;
 
-    // ---- phase A: target + re-warped source tiles with a 2-pixel halo, and the
-    //      upstream gradient of the per-channel SSIM values on the +1 ring ----
-    for (int cell = threadIdx.x; cell < T2::kCells; cell += kTileThreads) {
-        int cx, cy, ry, rx;
-        T2::cell_xy(cell, cx, cy);
-        float g1 = 0.f;
-        if (T2::cell_to_reflected(cell, x0, y0, H, W, ry, rx)) {
-            WarpPt p;
-            fill_cell(c, cam, A, rx, ry, ts, ws, T2::kCells, cell, p);
-            const int gx = x0 + cx, gy = y0 + cy;
-            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {      // a real output pixel q
-                const int pix = gy * W + gx;
-                float Gd = sc.c_rep * __ldg(mask + pix);
-                if (gdiff) Gd += __ldg(gdiff + pix);
-                if (depth_mask) Gd *= (1.0f - depth_inconsistency(p.Z, sample_plane(c.rdep, p, H, W)));
-                g1 = Gd * A.third * L.w_ssim;
-            }
-        } else {
-            zero_cell(ts, ws, T2::kCells, cell);
-        }
-        if (cx >= -1 && cx <= kTileW && cy >= -1 && cy <= kTileH) G1[T1::cell(cx, cy)] = g1;
+    // ---- phase B: coefficients of the tile + 1 ring, scaled by the upstream gradient of
+    //      diff_img at their pixel q (zero outside the image) ----
+    for (int cell = threadIdx.x; cell < T1::kCells; cell += kTileThreads) {
+        int cx, cy;
+        T1::cell_xy(cell, cx, cy);
+        const int qx = x0 + cx, qy = y0 + cy;
+        float Gd = 0.f;
+        const bool inside = qx >= 0 && qx < W && qy >= 0 && qy < H;
+        const int pix = qy * W + qx;
+        if (inside) Gd = upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, __ldg(mask + pix));
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+            cs[j * T1::kCells + cell] = (inside && Gd != 0.f) ? Gd * __ldg(coef + (int64_t)j * n + pix) : 0.f;
     }
     __syncthreads();
 
-    float gw[kPixPerThread][3];      // grad wrt the warped image at the own pixels
-    float d0[kPixPerThread];         // un-weighted photometric error (depth-mask only)
+    // ---- phase C: separable 3x3 sums of the nine coefficient planes down the strip.
+    //      Reflection padding folds window taps that fall outside the image back onto
+    //      row/column 1 and H-2/W-2: those receive the border neighbour twice. ----
+    float V[kPixPerThread][9];
+    {
+        float h[kPixPerThread + 2][9];
+        const bool dup_l = (gx == 1), dup_r = (gx == W - 2);
 #pragma unroll
-    for (int k = 0; k < kPixPerThread; ++k) { gw[k][0] = gw[k][1] = gw[k][2] = 0.f; d0[k] = 0.f; }
-
-    for (int ch = 0; ch < 3; ++ch) {
-        const float* tch = ts + ch * T2::kCells;
-        const float* wch = ws + ch * T2::kCells;
-        // ---- phase B: SSIM adjoint coefficients of this channel on the +1 ring ----
-        for (int cell = threadIdx.x; cell < T1::kCells; cell += kTileThreads) {
-            int cx, cy;
-            T1::cell_xy(cell, cx, cy);
-            const float g1 = G1[cell];
-            const int gx = x0 + cx, gy = y0 + cy;
-            float a = 0.f, bb = 0.f, cc = 0.f, val = 0.f;
-            if (gx >= 0 && gx < W && gy >= 0 && gy < H && (g1 != 0.f || depth_mask)) {
-                const int c2 = T2::cell(cx, cy);
-                const SsimStats s = ssim_stats(tch + c2, wch + c2, T2::kPitch);
-                const SsimTerms t = ssim_terms(s, L.C1, L.C2);
-                const SsimCoef k = ssim_coef(s, t, g1);       // x = target, y = warped
-                a = k.Ay; bb = k.B; cc = k.Cc;
-                val = clamp01_nan(t.raw);
+        for (int r = 0; r < kPixPerThread + 2; ++r) {
+            const int c1 = T1::cell(tx, ty0 - 1 + r);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const float* pl = cs + j * T1::kCells + c1;
+                const float l = pl[-1], m = pl[0], rr = pl[1];
+                float s = (l + m) + rr;
+                if (dup_l) s += l;
+                if (dup_r) s += rr;
+                h[r][j] = s;
             }
-            cA[cell] = a; cB[cell] = bb; cC[cell] = cc; sv[cell] = val;
         }
-        __syncthreads();
-        // ---- phase C: gather the 3x3 coefficient neighbourhood of each own pixel ----
 #pragma unroll
         for (int k = 0; k < kPixPerThread; ++k) {
-            int tx, ty;
-            own_pixel(threadIdx.x, k, tx, ty);
-            const int gx = x0 + tx, gy = y0 + ty;
-            if (gx < W && gy < H) {
-                float sA = 0.f, sB = 0.f, sC = 0.f;
+            const int gy = y0 + ty0 + k;
+            const bool dup_u = (gy == 1), dup_d = (gy == H - 2);
 #pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int my = reflect_mult(gy + dy, gy, H);
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const float m = (float)(my * reflect_mult(gx + dx, gx, W));
-                        const int c1 = T1::cell(tx + dx, ty + dy);
-                        sA += m * cA[c1]; sB += m * cB[c1]; sC += m * cC[c1];
-                    }
-                }
-                const int c2 = T2::cell(tx, ty);
-                const float t = tch[c2], w = wch[c2];
-                gw[k][ch] = sA + 2.0f * w * sB + t * sC;
-                if (depth_mask) {
-                    const float l1 = clamp01_nan(fabsf(__fsub_rn(t, w)));
-                    d0[k] += __fadd_rn(__fmul_rn(l1, L.w_l1), __fmul_rn(sv[T1::cell(tx, ty)], L.w_ssim));
-                }
+            for (int j = 0; j < 9; ++j) {
+                float s = (h[k][j] + h[k + 1][j]) + h[k + 2][j];
+                if (dup_u) s += h[k][j];
+                if (dup_d) s += h[k + 2][j];
+                V[k][j] = s;
             }
         }
-        __syncthreads();
     }
 
     // ---- phase D: L1 / depth adjoints and the geometry adjoint per own pixel ----
@@ -294,57 +373,55 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     for (int i = 0; i < 12; ++i) acc[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
-        int tx, ty;
-        own_pixel(threadIdx.x, k, tx, ty);
-        const int gx = x0 + tx, gy = y0 + ty;
+        const int gy = y0 + ty0 + k;
         if (gx < W && gy < H) {
             const int pix = gy * W + gx;
-            const int c2 = T2::cell(tx, ty);
             WarpPt p;
             warp_point(cam, A, gx, gy, __ldg(c.tdep + pix), p);
+            const TapIdx ti = make_taps(p, H, W);
             const float m = __ldg(mask + pix);
-            float Gd = sc.c_rep * m;
-            if (gdiff) Gd += __ldg(gdiff + pix);
+            const float Gd = upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, m);
             float pd = 0.f, dd = 0.f;
             Taps td;
             if (need_depth) {
-                td = gather_taps(c.rdep, p, H, W);
-                pd = bilinear(td, p);
+                td = load_taps(c.rdep, ti, W);
+                pd = blend(td, ti);
                 dd = depth_inconsistency(p.Z, pd);
             }
             float G0 = Gd, Gdd = sc.c_dep * m;
             if (depth_mask) {
                 G0 = Gd * (1.0f - dd);
-                Gdd -= Gd * (d0[k] * A.third);
+                Gdd -= Gd * __ldg(coef + (int64_t)9 * n + pix);
             }
             float g_ix = 0.f, g_iy = 0.f;
             const float gl1 = G0 * A.third * L.w_l1;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const float t = ts[ch * T2::kCells + c2], w = ws[ch * T2::kCells + c2];
+                const Taps tv = load_taps(c.ref + ch * c.ref_sc, ti, W);
+                const float w = blend(tv, ti);
+                const float t = __ldg(c.tgt + ch * c.tgt_sc + pix);
                 const float dlt = t - w;
-                float gwc = gw[k][ch];
+                float gwc = V[k][3 * ch] + 2.0f * w * V[k][3 * ch + 1] + t * V[k][3 * ch + 2];
                 if (fabsf(dlt) <= 1.0f) gwc += (dlt > 0.f) ? -gl1 : ((dlt < 0.f) ? gl1 : 0.f);
-                const Taps ti = gather_taps(c.ref + ch * c.ref_sc, p, H, W);
-                bilinear_grad(ti, p, gwc, g_ix, g_iy);
+                bilinear_grad(tv, p, gwc, g_ix, g_iy);
             }
             float g_Z = 0.f, g_pd = 0.f;
             if (need_depth && Gdd != 0.f) {
                 depth_inconsistency_adjoint(p.Z, pd, Gdd, g_Z, g_pd);
                 bilinear_grad(td, p, g_pd, g_ix, g_iy);
                 if (g.g_ref_depth && g_pd != 0.f) {
-                    float* plane = g.g_ref_depth + (int64_t)b * n;
-                    const bool x0in = (p.x0 >= 0) && (p.x0 < W), x1in = (p.x0 + 1 >= 0) && (p.x0 + 1 < W);
-                    const bool y0in = (p.y0 >= 0) && (p.y0 < H), y1in = (p.y0 + 1 >= 0) && (p.y0 + 1 < H);
-                    float* r0 = plane + (int64_t)p.y0 * W + p.x0;
-                    if (y0in && x0in) atomicAdd(r0, g_pd * (p.wx0 * p.wy0));
-                    if (y0in && x1in) atomicAdd(r0 + 1, g_pd * (p.wx1 * p.wy0));
-                    if (y1in && x0in) atomicAdd(r0 + W, g_pd * (p.wx0 * p.wy1));
-                    if (y1in && x1in) atomicAdd(r0 + W + 1, g_pd * (p.wx1 * p.wy1));
+                    float* r0 = g.g_ref_depth + (int64_t)b * n + ti.off;
+                    if (ti.nw) atomicAdd(r0, g_pd * ti.w_nw);
+                    if (ti.ne) atomicAdd(r0 + 1, g_pd * ti.w_ne);
+                    if (ti.sw) atomicAdd(r0 + W, g_pd * ti.w_sw);
+                    if (ti.se) atomicAdd(r0 + W + 1, g_pd * ti.w_se);
                 }
             }
             const GeomGrad gg = geom_adjoint(cam, A, p, g_ix, g_iy, g_Z);
-            if (g.g_tgt_depth) g.g_tgt_depth[(int64_t)b * n + pix] = gg.g_depth;
+            if (g.g_tgt_depth) {
+                if (shared_grads) atomicAdd(g.g_tgt_depth + (int64_t)b * n + pix, gg.g_depth);
+                else g.g_tgt_depth[(int64_t)b * n + pix] = gg.g_depth;
+            }
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 acc[i * 4 + 0] += gg.gp[i] * p.cam[0];
@@ -361,6 +438,7 @@ static int fill_launch(PairLaunch& L, const tcsfm_pair_group* groups, int n, int
                        float w_l1, float w_ssim, int flags, const char* who, bool bwd) {
     if (B <= 0 || H < 2 || W < 2) { set_error("%s: bad shape B=%d H=%d W=%d", who, B, H, W); return 1; }
     if (B > 65535) { set_error("%s: B=%d exceeds 65535", who, B); return 1; }
+    if ((int64_t)H * W * kCoefPlanes >= (int64_t)1 << 31) { set_error("%s: image too large", who); return 1; }
     if (!(flags & TCSFM_SSIM)) { set_error("%s: the fused pair loss requires TCSFM_SSIM (l_ssim)", who); return 1; }
     const bool need_depth = (flags & (TCSFM_DEPTH_MASK | TCSFM_DEPTH_CONSIST)) != 0;
     for (int i = 0; i < n; ++i) {
@@ -369,7 +447,7 @@ static int fill_launch(PairLaunch& L, const tcsfm_pair_group* groups, int n, int
             set_error("%s: group %d has a null input pointer", who, i); return 1;
         }
         if (need_depth && !g.ref_depth) { set_error("%s: group %d needs ref_depth for the depth terms", who, i); return 1; }
-        if (bwd && !g.mask) { set_error("%s: group %d: backward needs the forward mask", who, i); return 1; }
+        if (bwd && (!g.mask || !g.coef)) { set_error("%s: group %d: backward needs the forward's mask and coef workspace", who, i); return 1; }
         L.g[i] = g;
     }
     L.A = make_arith(H, W, flags);
@@ -383,10 +461,12 @@ static int fill_launch(PairLaunch& L, const tcsfm_pair_group* groups, int n, int
 
 using namespace tcsfm;
 
+extern "C" int tcsfm_pair_coef_planes(void) { return kCoefPlanes; }
+
 extern "C" int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
                                    float w_l1, float w_ssim, int flags, void* stream) {
     if (!groups || n_groups <= 0) { set_error("tcsfm_pair_loss_fwd: no groups"); return 1; }
-    const size_t smem = 6 * Tile<1>::kCells * sizeof(float);
+    const size_t smem = 3 * Tile<1>::kCells * sizeof(float2);
     const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
     for (int base = 0; base < n_groups; base += kMaxGroups) {
         const int n = (n_groups - base < kMaxGroups) ? n_groups - base : kMaxGroups;
@@ -404,13 +484,7 @@ extern "C" int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
 extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
                                    float w_l1, float w_ssim, int flags, void* stream) {
     if (!groups || n_groups <= 0) { set_error("tcsfm_pair_loss_bwd: no groups"); return 1; }
-    const size_t smem = (6 * Tile<2>::kCells + 5 * Tile<1>::kCells) * sizeof(float);
-#ifndef TCSFM_HOST_EMU
-    {   // > 48 KB of dynamic shared memory is opt-in (per device, so set it on every call)
-        cudaError_t e = cudaFuncSetAttribute(pair_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("tcsfm_pair_loss_bwd: cannot raise dynamic smem to %zu: %s", smem, cudaGetErrorString(e)); return 2; }
-    }
-#endif
+    const size_t smem = 9 * Tile<1>::kCells * sizeof(float);
     const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
     for (int base = 0; base < n_groups; base += kMaxGroups) {
         const int n = (n_groups - base < kMaxGroups) ? n_groups - base : kMaxGroups;
@@ -418,7 +492,10 @@ extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
         memset(&L, 0, sizeof(L));
         if (int rc = fill_launch(L, groups + base, n, B, H, W, w_l1, w_ssim, flags, "tcsfm_pair_loss_bwd", true)) return rc;
         for (int i = 0; i < n; ++i) {
-            if (L.g[i].g_ref_depth) cudaMemsetAsync(L.g[i].g_ref_depth, 0, (size_t)B * H * W * sizeof(float), (cudaStream_t)stream);
+            if (L.g[i].min_base && (!L.g[i].g_min || L.g[i].min_count < 1 || L.g[i].min_index >= L.g[i].min_count)) {
+                set_error("tcsfm_pair_loss_bwd: group %d: inconsistent min-reprojection fields", base + i); return 1;
+            }
+            if (L.g[i].g_ref_depth && !(flags & TCSFM_SHARED_GRADS)) cudaMemsetAsync(L.g[i].g_ref_depth, 0, (size_t)B * H * W * sizeof(float), (cudaStream_t)stream);
             if (L.g[i].g_proj) cudaMemsetAsync(L.g[i].g_proj, 0, (size_t)B * 12 * sizeof(float), (cudaStream_t)stream);
         }
         dim3 grid(tiles, B, n), block(kTileThreads);

@@ -51,6 +51,23 @@ def get_smooth_loss(disp, img):
     return grad_disp_x.mean() + grad_disp_y.mean()
 
 
+_KINV_CACHE = {}
+
+
+def inverse_intrinsics(intrinsics):
+    """`intrinsics.inverse()` (models/stn.py:257), memoised per tensor version: K is a loader
+    output that stays constant across the warps/losses of a step, and the batched LU costs
+    half a dozen launches."""
+    key = (intrinsics.data_ptr(), intrinsics._version, intrinsics.device, tuple(intrinsics.shape))
+    hit = _KINV_CACHE.get(key)
+    if hit is None:
+        if len(_KINV_CACHE) > 64:
+            _KINV_CACHE.clear()
+        hit = (intrinsics.detach().inverse(), intrinsics)      # keeps K alive so the pointer stays unique
+        _KINV_CACHE[key] = hit
+    return hit[0]
+
+
 def _pair_flags(config):
     flags = _cabi.SSIM
     if config['with_auto_mask'] == True:    # noqa: E712 -- the reference compares with ==
@@ -85,7 +102,7 @@ class Compute_Loss(nn.modules.Module):
             raise NotImplementedError("the fused pair loss implements the l_ssim=True configuration "
                                       "(the default of every reference script)")
         n = len(specs)
-        kinv = intrinsics.inverse()                                  # models/stn.py:257
+        kinv = inverse_intrinsics(intrinsics)                        # models/stn.py:257
         poses = torch.cat([s[4][:, 0:6] for s in specs], 0)          # [n*B, 6]
         proj = intrinsics.repeat(n, 1, 1) @ pose_vec2mat(poses)      # models/stn.py:259-262
         tensors = []
@@ -95,6 +112,35 @@ class Compute_Loss(nn.modules.Module):
         diff, mask, l_rep, l_dep = ops.PairLossFn.apply(cfg, n, kinv, proj, *tensors)
         want_depth = self.config['l_depth_consist'] == True          # noqa: E712
         return [(l_rep[i], l_dep[i] if want_depth else 0, diff[i], mask[i]) for i in range(n)]
+
+    def _can_fuse_frame(self, specs, intrinsics):
+        return (self.config['l_ssim'] == True and not intrinsics.requires_grad      # noqa: E712
+                and len(specs) <= 8 and len(specs) * intrinsics.shape[0] >= 2
+                and all(s[0].shape == specs[0][0].shape and s[1].shape == specs[0][0].shape for s in specs))
+
+    def _frame_terms(self, specs, roles, intrinsics):
+        """All pair evaluations of one scale plus the min-reprojection / mean-on-mask reductions
+        as one fused autograd node.  `specs` carry the un-negated poses.  Returns the [3]
+        tensor (l_reconstruct_inverse, l_reconstruct_forward, l_depth)."""
+        images, depths = [], []
+
+        def index(lst, t):
+            for i, u in enumerate(lst):
+                if u is t:
+                    return i
+            lst.append(t)
+            return len(lst) - 1
+        groups = []
+        for role, (tgt_img, ref_img, tgt_depth, ref_depth, _) in zip(roles, specs):
+            groups.append((0 if role == 'inv' else 1, index(images, tgt_img), index(images, ref_img),
+                           index(depths, tgt_depth), index(depths, ref_depth)))
+        want_depth = self.config['l_depth_consist'] == True          # noqa: E712
+        meta = {"w_l1": float(self.config['l1_weight']), "w_ssim": float(self.config['l_ssim_weight']),
+                "flags": _pair_flags(self.config), "w_inverse": 0.3,
+                "w_depth": float(self.l_depth_consist_weight) if want_depth else 0.0,
+                "n_img": len(images), "groups": groups}
+        poses = torch.cat([s[4][:, 0:6] for s in specs], 0)
+        return ops.FrameLossFn.apply(meta, inverse_intrinsics(intrinsics), intrinsics, poses, *images, *depths)
 
     def forward(self, source_imgs, target_img, poses, disparity, intrinsics, pose_vec_weight=None,
                 validate=False, epoch=5, target_img_right=None):
@@ -122,11 +168,20 @@ class Compute_Loss(nn.modules.Module):
                     _, source_d = disp_to_depth(source_disparity, cfg['min_depth'], cfg['max_depth'])
                     if cfg['l_smooth']:
                         losses['l_smooth'] += (self.l_smooth_weight * get_smooth_loss(source_disparity, source_img)) / (2 ** scale)
+                    # the pose handed to the warp is the negated prediction (losses.py:112,119)
                     if cfg['l_inverse']:   # inverse reconstruction: target reprojected into the source frame
-                        specs.append((source_img, target_img, source_d, d, -poses_inv[j]))
+                        specs.append((source_img, target_img, source_d, d, poses_inv[j]))
                         roles.append('inv')
-                    specs.append((target_img, source_img, d, source_d, -poses[j]))
+                    specs.append((target_img, source_img, d, source_d, poses[j]))
                     roles.append('fwd')
+                if not self._can_fuse_frame(specs, intrinsics):
+                    specs = [s_[:4] + (-s_[4],) for s_ in specs]
+                if self._can_fuse_frame(specs, intrinsics):
+                    terms = self._frame_terms(specs, roles, intrinsics)
+                    losses['l_reconstruct_inverse'] += terms[0:1]
+                    losses['l_reconstruct_forward'] += terms[1:2]
+                    losses['l_depth'] += terms[2:3]
+                    continue
                 results = self._pair_groups(specs, intrinsics)
                 reconstruction_errors = []
                 for role, (l_reprojection, l_depth, diff_img, _) in zip(roles, results):

@@ -96,21 +96,23 @@ class PairLossFn(torch.autograd.Function):
         flags = flags | ARITH_FLAGS
         with _guard(kinv):
             batch = _raw.PairBatch(groups)
-            diff, mask, sums = _raw.pair_loss_fwd(lib(), batch, w_l1, w_ssim, flags)
+            want_grad = any(ctx.needs_input_grad)
+            diff, mask, sums, coef = _raw.pair_loss_fwd(lib(), batch, w_l1, w_ssim, flags, want_grad=want_grad)
         # mean_on_mask (losses.py:142-149) without the host round trip
         enough = sums[:, 1] > 10000
         zero = torch.zeros_like(sums[:, 0])
         l_rep = torch.where(enough, sums[:, 0] / sums[:, 1], zero)
         l_dep = torch.where(enough, sums[:, 2] / sums[:, 1], zero)
         ctx.batch, ctx.cfg, ctx.flags, ctx.n_groups = batch, (w_l1, w_ssim), flags, n_groups
-        ctx.save_for_backward(mask, sums)
+        if want_grad:
+            ctx.save_for_backward(mask, sums, coef)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(mask)
         return diff, mask, l_rep, l_dep
 
     @staticmethod
     def backward(ctx, g_diff, g_mask, g_lrep, g_ldep):
-        mask, sums = ctx.saved_tensors
+        mask, sums, coef = ctx.saved_tensors
         g_scalars = None
         if g_lrep is not None or g_ldep is not None:
             z = torch.zeros_like(sums[:, 0])
@@ -118,9 +120,91 @@ class PairLossFn(torch.autograd.Function):
                                      g_ldep if g_ldep is not None else z], dim=1)
         need_ref = (ctx.flags & (_cabi.DEPTH_MASK | _cabi.DEPTH_CONSIST)) != 0
         with _guard(mask):
-            g_td, g_rd, g_proj = _raw.pair_loss_bwd(lib(), ctx.batch, mask, sums, g_diff, g_scalars,
+            g_td, g_rd, g_proj = _raw.pair_loss_bwd(lib(), ctx.batch, mask, sums, coef, g_diff, g_scalars,
                                                     ctx.cfg[0], ctx.cfg[1], ctx.flags, need_ref)
         grads = [None, None, None, g_proj.reshape(-1, 3, 4)]
         for i in range(ctx.n_groups):
             grads += [None, None, g_td[i], g_rd[i] if need_ref else None]
         return tuple(grads)
+
+
+class PoseProjFn(torch.autograd.Function):
+    """pose [N,6] (multiplied by `sign`), K [Bk,3,3] -> K @ [Rx Ry Rz | t] as [N,3,4]
+    (csrc/frame_kernels.cu); one launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, pose, K, sign):
+        _require_cuda(pose, K)
+        with _guard(pose):
+            proj = _raw.pose_proj_fwd(lib(), pose, K, sign)
+        ctx.save_for_backward(pose, K)
+        ctx.sign = sign
+        return proj
+
+    @staticmethod
+    def backward(ctx, g_proj):
+        pose, K = ctx.saved_tensors
+        with _guard(pose):
+            g_pose = _raw.pose_proj_bwd(lib(), pose, K, ctx.sign, g_proj)
+        return g_pose, None, None
+
+
+class FrameLossFn(torch.autograd.Function):
+    """The reconstruction terms of one scale of Compute_Loss.forward (losses.py:99-132) as
+    five launches forward (pose->K[R|t], pair kernel, min-reduce, finalize + memsets) and four
+    backward (prepare, pair kernel, pose chain rule + memsets).
+
+    apply(meta, kinv, K, poses [G*B,6], *images, *depths) -> [3] =
+    (l_reconstruct_inverse, l_reconstruct_forward, l_depth) before the division by num_scales.
+    meta: dict(w_l1, w_ssim, flags, w_inverse, w_depth, n_img, groups=[(role, tgt_img, ref_img,
+    tgt_depth, ref_depth)]) with indices into `images` / `depths`; role 0 = inverse, 1 = forward."""
+
+    @staticmethod
+    def forward(ctx, meta, kinv, K, poses, *tensors):
+        _require_cuda(kinv, K, poses, *tensors)
+        images, depths = tensors[:meta["n_img"]], tensors[meta["n_img"]:]
+        groups = meta["groups"]
+        g, b = len(groups), K.shape[0]
+        flags = meta["flags"] | ARITH_FLAGS
+        with _guard(K):
+            kinv = kinv.contiguous()
+            proj = _raw.pose_proj_fwd(lib(), poses, K, -1.0)
+            specs = [{"tgt_img": images[ti], "ref_img": images[ri], "tgt_depth": depths[td], "ref_depth": depths[rd],
+                      "kinv": kinv, "proj": proj[i * b:(i + 1) * b]} for i, (_, ti, ri, td, rd) in enumerate(groups)]
+            batch = _raw.PairBatch(specs)
+            want_grad = any(ctx.needs_input_grad)
+            diff, mask, sums, coef = _raw.pair_loss_fwd(lib(), batch, meta["w_l1"], meta["w_ssim"], flags, want_grad=want_grad)
+            fwd_idx = [i for i, grp in enumerate(groups) if grp[0] == 1]
+            step = fwd_idx[1] - fwd_idx[0] if len(fwd_idx) > 1 else 1
+            if any(fwd_idx[k + 1] - fwd_idx[k] != step for k in range(len(fwd_idx) - 1)):
+                raise ValueError("forward groups must be evenly spaced")
+            n_px = diff[0].numel()
+            min_sum = None
+            if fwd_idx:
+                min_sum = _raw.min_reduce(lib(), diff[fwd_idx[0]], step * n_px, len(fwd_idx), n_px)
+            cfg = _raw.make_frame_cfg([grp[0] for grp in groups], meta["w_inverse"], meta["w_depth"], n_px)
+            out = _raw.frame_finalize(lib(), sums, min_sum, cfg)
+        if want_grad:
+            ctx.save_for_backward(mask, sums, coef, diff, poses, K)
+            ctx.batch, ctx.cfg, ctx.meta, ctx.flags = batch, cfg, meta, flags
+            ctx.min_info = (fwd_idx, step * n_px)
+            ctx.n_dep, ctx.dep_shape = len(depths), depths[0].shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        mask, sums, coef, diff, poses, K = ctx.saved_tensors
+        meta, groups = ctx.meta, ctx.meta["groups"]
+        fwd_idx, stride = ctx.min_info
+        need_ref = (ctx.flags & (_cabi.DEPTH_MASK | _cabi.DEPTH_CONSIST)) != 0
+        with _guard(K):
+            g_scalars, g_min = _raw.frame_bwd_prepare(lib(), g_out, ctx.cfg)
+            g_depths = torch.empty((ctx.n_dep,) + tuple(ctx.dep_shape), dtype=torch.float32, device=K.device)
+            min_pos = [fwd_idx.index(i) if i in fwd_idx else -1 for i in range(len(groups))]
+            min_first = diff[fwd_idx[0]] if fwd_idx else None
+            g_proj = _raw.pair_loss_bwd_shared(
+                lib(), ctx.batch, mask, sums, coef, g_scalars, g_min, (min_first, stride, min_pos, len(fwd_idx)),
+                g_depths, [grp[3] for grp in groups], [grp[4] for grp in groups],
+                meta["w_l1"], meta["w_ssim"], ctx.flags, need_ref)
+            g_pose = _raw.pose_proj_bwd(lib(), poses, K, -1.0, g_proj.reshape(-1, 3, 4))
+        return (None, None, None, g_pose) + (None,) * meta["n_img"] + tuple(g_depths[i] for i in range(ctx.n_dep))
