@@ -232,12 +232,42 @@ def main():
         else:
             run_step(loss_mod, sets[i % N_INPUT_SETS], n_src)
 
+    # End-to-end arm: every step copies its inputs from pinned host memory and reads the loss
+    # back to the host.  Two device-side input buffers are used so that the copy of step i+1
+    # (copy stream) overlaps the compute of step i (graph replay on the main stream); the loss
+    # of step i is read on the host while step i+1 runs.
     loss_holder = [0.0]
+    e2e = None
+    if graphs is not None:
+        copy_stream = torch.cuda.Stream()
+        e2e = {"in": [graphs[0], graphs[1]], "bufs": [sets[0], sets[1]],
+               "h2d_done": [torch.cuda.Event(), torch.cuda.Event()],
+               "compute_done": [torch.cuda.Event(), torch.cuda.Event()],
+               "loss_host": [torch.zeros((), pin_memory=True), torch.zeros((), pin_memory=True)]}
+        for ev in e2e["compute_done"]:
+            ev.record()
 
     def step_e2e(i):
         h = host_sets[i % 2]
-        inp = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
-        loss_holder[0] = float(run_step(loss_mod, inp, n_src).detach())   # device -> host read of the loss
+        if e2e is None:
+            inp = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+            loss_holder[0] = float(run_step(loss_mod, inp, n_src).detach())   # device -> host read of the loss
+            return
+        k = i % 2
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            copy_stream.wait_event(e2e["compute_done"][k])          # buffer k is free again
+            for name, src in h.items():
+                e2e["bufs"][k][name].copy_(src, non_blocking=True)
+            e2e["h2d_done"][k].record(copy_stream)
+        main = torch.cuda.current_stream()
+        main.wait_event(e2e["h2d_done"][k])
+        graph_k, loss_k = e2e["in"][k]
+        graph_k.replay()
+        e2e["loss_host"][k].copy_(loss_k.detach(), non_blocking=True)
+        e2e["compute_done"][k].record(main)
+        if i > 0:                                                     # read the previous step's loss
+            e2e["compute_done"][1 - k].synchronize()
+            loss_holder[0] = float(e2e["loss_host"][1 - k])
 
     for i in range(args.warmup):
         step_resident(i)

@@ -27,8 +27,12 @@
 
 namespace tcsfm {
 
-#ifndef TCSFM_PAIR_MIN_BLOCKS
-#define TCSFM_PAIR_MIN_BLOCKS 2      // resident CTAs per SM the register allocation targets
+// resident CTAs per SM the register allocation targets (256 threads each)
+#ifndef TCSFM_FWD_MIN_BLOCKS
+#define TCSFM_FWD_MIN_BLOCKS 4
+#endif
+#ifndef TCSFM_BWD_MIN_BLOCKS
+#define TCSFM_BWD_MIN_BLOCKS 2
 #endif
 
 constexpr int kMaxGroups = 8;
@@ -123,7 +127,7 @@ __device__ __forceinline__ void ring_cell(int r, int& cx, int& cy) {
     else { cx = kTileW; cy = r - 2 * (kTileW + 2) - kTileH; }
 }
 
-__global__ void __launch_bounds__(kTileThreads, TCSFM_PAIR_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTileThreads, TCSFM_FWD_MIN_BLOCKS)
 pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
     using T1 = Tile<1>;
     TCSFM_DYN_SMEM(float2, tw);                       // [3][T1::kCells] (target, warped)
@@ -196,26 +200,28 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const float2* plane = tw + ch * T1::kCells;
-        float2 v[kPixPerThread + 2][3], sq[kPixPerThread + 2][3];
-        float ab[kPixPerThread + 2][3];
+        // rolling 3-row window of (target, warped) taps; squares / products are formed per use
+        // (cheaper than keeping 27 more registers live across the strip)
+        float2 v[3][3];
 #pragma unroll
-        for (int r = 0; r < kPixPerThread + 2; ++r) {
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-                v[r][cc] = plane[T1::cell(tx - 1 + cc, ty0 - 1 + r)];
-                sq[r][cc] = square2_rn(v[r][cc]);
-                ab[r][cc] = __fmul_rn(v[r][cc].x, v[r][cc].y);
-            }
-        }
+            for (int cc = 0; cc < 3; ++cc) v[r][cc] = plane[T1::cell(tx - 1 + cc, ty0 - 1 + r)];
 #pragma unroll
         for (int k = 0; k < kPixPerThread; ++k) {
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) v[(k + 2) % 3][cc] = plane[T1::cell(tx - 1 + cc, ty0 + 1 + k)];
             float2 wv[9], wsq[9];
             float wab[9];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) { wv[i] = v[k + i / 3][i % 3]; wsq[i] = sq[k + i / 3][i % 3]; wab[i] = ab[k + i / 3][i % 3]; }
+            for (int i = 0; i < 9; ++i) {
+                wv[i] = v[(k + i / 3) % 3][i % 3];
+                wsq[i] = square2_rn(wv[i]);
+                wab[i] = __fmul_rn(wv[i].x, wv[i].y);
+            }
             const SsimStats s = ssim_stats_packed(wv, wsq, wab);
             const SsimTerms t = ssim_terms(s, L.C1, L.C2);
-            const float2 ctr = v[k + 1][1];
+            const float2 ctr = wv[4];
             const float l1 = clamp01_nan(fabsf(__fsub_rn(ctr.x, ctr.y)));
             const float e = __fadd_rn(__fmul_rn(l1, L.w_l1), __fmul_rn(clamp01_nan(t.raw), L.w_ssim));
             esum[k] = (ch == 0) ? e : __fadd_rn(esum[k], e);
@@ -290,7 +296,7 @@ __device__ __forceinline__ float upstream_diff(const tcsfm_pair_group& g, const 
     return Gd;
 }
 
-__global__ void __launch_bounds__(kTileThreads, TCSFM_PAIR_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTileThreads, TCSFM_BWD_MIN_BLOCKS)
 pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     using T1 = Tile<1>;
     TCSFM_DYN_SMEM(float, cs);                     // [9][T1::kCells] upstream-scaled coefficients
@@ -329,52 +335,48 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         if (inside) Gd = upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, __ldg(mask + pix));
 #pragma unroll
         for (int j = 0; j < 9; ++j)
-            cs[j * T1::kCells + cell] = (inside && Gd != 0.f) ? Gd * __ldg(coef + (int64_t)j * n + pix) : 0.f;
+            cs[j * T1::kCells + cell] = inside ? Gd * __ldg(coef + (int64_t)j * n + pix) : 0.f;
     }
     __syncthreads();
 
-    // ---- phase C: separable 3x3 sums of the nine coefficient planes down the strip.
-    //      Reflection padding folds window taps that fall outside the image back onto
-    //      row/column 1 and H-2/W-2: those receive the border neighbour twice. ----
-    float V[kPixPerThread][9];
-    {
-        float h[kPixPerThread + 2][9];
-        const bool dup_l = (gx == 1), dup_r = (gx == W - 2);
-#pragma unroll
-        for (int r = 0; r < kPixPerThread + 2; ++r) {
-            const int c1 = T1::cell(tx, ty0 - 1 + r);
-#pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                const float* pl = cs + j * T1::kCells + c1;
-                const float l = pl[-1], m = pl[0], rr = pl[1];
-                float s = (l + m) + rr;
-                if (dup_l) s += l;
-                if (dup_r) s += rr;
-                h[r][j] = s;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kPixPerThread; ++k) {
-            const int gy = y0 + ty0 + k;
-            const bool dup_u = (gy == 1), dup_d = (gy == H - 2);
-#pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                float s = (h[k][j] + h[k + 1][j]) + h[k + 2][j];
-                if (dup_u) s += h[k][j];
-                if (dup_d) s += h[k + 2][j];
-                V[k][j] = s;
-            }
-        }
-    }
-
-    // ---- phase D: L1 / depth adjoints and the geometry adjoint per own pixel ----
+    // ---- phases C + D, one own pixel at a time down the strip.
+    //      C: separable 3x3 sums of the nine coefficient planes with a rolling window of
+    //         horizontal 3-sums.  Reflection padding folds window taps that fall outside the
+    //         image back onto row/column 1 and H-2/W-2: those receive the border neighbour twice.
+    //      D: L1 / depth adjoints and the geometry adjoint. ----
     float acc[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+    float h[3][9];
+    const bool dup_l = (gx == 1), dup_r = (gx == W - 2);
+    auto hsum = [&](int r, float (&out)[9]) {          // horizontal 3-sums of tile row ty0 - 1 + r
+        const int c1 = T1::cell(tx, ty0 - 1 + r);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const float* pl = cs + j * T1::kCells + c1;
+            const float l = pl[-1], m = pl[0], rr = pl[1];
+            float s = (l + m) + rr;
+            if (dup_l) s += l;
+            if (dup_r) s += rr;
+            out[j] = s;
+        }
+    };
+    hsum(0, h[0]);
+    hsum(1, h[1]);
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
+        hsum(k + 2, h[(k + 2) % 3]);
         const int gy = y0 + ty0 + k;
         if (gx < W && gy < H) {
+            float V[9];
+            const bool dup_u = (gy == 1), dup_d = (gy == H - 2);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                float s = (h[k % 3][j] + h[(k + 1) % 3][j]) + h[(k + 2) % 3][j];
+                if (dup_u) s += h[k % 3][j];
+                if (dup_d) s += h[(k + 2) % 3][j];
+                V[j] = s;
+            }
             const int pix = gy * W + gx;
             WarpPt p;
             warp_point(cam, A, gx, gy, __ldg(c.tdep + pix), p);
@@ -401,7 +403,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
                 const float w = blend(tv, ti);
                 const float t = __ldg(c.tgt + ch * c.tgt_sc + pix);
                 const float dlt = t - w;
-                float gwc = V[k][3 * ch] + 2.0f * w * V[k][3 * ch + 1] + t * V[k][3 * ch + 2];
+                float gwc = V[3 * ch] + 2.0f * w * V[3 * ch + 1] + t * V[3 * ch + 2];
                 if (fabsf(dlt) <= 1.0f) gwc += (dlt > 0.f) ? -gl1 : ((dlt < 0.f) ? gl1 : 0.f);
                 bilinear_grad(tv, p, gwc, g_ix, g_iy);
             }

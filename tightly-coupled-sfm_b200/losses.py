@@ -146,7 +146,7 @@ class Compute_Loss(nn.modules.Module):
                 validate=False, epoch=5, target_img_right=None):
         """Reference losses.py:75-140.  Returns the dict of [1]-shaped tensors
         l_reconstruct_inverse, l_reconstruct_forward, l_depth, l_smooth, total."""
-        zero = torch.zeros(1).type_as(intrinsics)
+        zero = torch.zeros(1, dtype=intrinsics.dtype, device=intrinsics.device)   # (reference: torch.zeros(1).type_as)
         losses = {'l_reconstruct_inverse': zero.clone(), 'l_reconstruct_forward': zero.clone(),
                   'l_depth': zero.clone(), 'l_smooth': zero.clone()}
         disparity, source_disparities = disparity[0], disparity[1:]
