@@ -31,6 +31,14 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+PFT_WORKLOADS = {
+    # sequential per-frame test-time optimisation (configs 3/4 of BASELINE.json); stand-in networks
+    "pft": dict(b=6, h=192, w=640, n_src=2, iterations=4, epochs=20,
+                desc="pft_kitti_windows_b6_192x640_4iter_20epochs_standin_nets"),
+    "pft-scannet": dict(b=16, h=256, w=320, n_src=1, iterations=4, epochs=20,
+                        desc="pft_scannet_pairs_b16_256x320_4iter_20epochs_standin_nets"),
+}
+
 WORKLOADS = {
     # name: (B, H, W, n_src, depth_range key, intrinsics)
     "kitti": dict(b=8, h=192, w=640, n_src=2, desc="kitti_triplets_b8_192x640_fwd+inv_ssim_l1_automask_depthconsist"),
@@ -130,17 +138,132 @@ def cpu_port_throughput(wl, steps, warmup, threads):
     return wl["b"] * steps / dt, dt / steps * 1e3
 
 
+def main_pft(args):
+    """PFT frames/s: every rank optimises its own contiguous shard of window minibatches
+    (tcsfm_b200.shard), no communication; a 'step' is one window minibatch taken through all
+    optimisation epochs (depth-net -> solve_pose_iteratively -> loss -> backward -> Adam)."""
+    wl = PFT_WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from tcsfm_b200 import pft_driver, shard, synth
+    opts = {"epochs": wl["epochs"], "num_source_imgs": wl["n_src"]}
+    rng = synth.KITTI_DEPTH_RANGE if wl["h"] == 192 else synth.SCANNET_DEPTH_RANGE
+    base = synth.KITTI_K if wl["h"] == 192 else synth.SCANNET_K
+    steps = min(args.steps, 4)
+    warm = min(args.warmup, 1)
+
+    def frames_for(seed, device):
+        return synth.make_frames(wl["b"], wl["h"], wl["w"], n_src=wl["n_src"], seed=seed, depth_range=rng,
+                                 intrinsics=torch.tensor(base, dtype=torch.float32), device=device)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import ref_torch as O
+
+        class OracleBackend:
+            solve_pose_iteratively = staticmethod(O.iterative_pose)
+            compute_optimization_loss = staticmethod(O.pft_window_loss)
+            disp_to_depth = staticmethod(O.disp_to_depth)
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu_opts = dict(opts, epochs=2)
+        fr = frames_for(0, "cpu")
+        dn, pn = synth.TinyDepthNet(0), synth.TinyPoseNet(0)
+        t0 = time.perf_counter()
+        pft_driver.optimize_window(dn, pn, fr["target"], fr["sources"], fr["K"], cpu_opts, wl["iterations"], rng, OracleBackend)
+        dt = (time.perf_counter() - t0) * wl["epochs"] / cpu_opts["epochs"]
+        fps = wl["b"] / dt
+        print(json.dumps({"impl": "reference", "metric": "PFT frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+                          "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"]},
+                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                           "sample": "2 of %d epochs of one window minibatch, extrapolated" % wl["epochs"]},
+                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from tcsfm_b200 import _timing
+    depth_net, pose_net = synth.TinyDepthNet(0).to(dev), synth.TinyPoseNet(0).to(dev)
+    total_mbs = steps * world
+    lo, hi = shard.shard_range(total_mbs, rank, world)           # this rank's window minibatches
+    data = [frames_for(1000 + i, dev) for i in range(lo, hi)]
+    host = [{k: ([t.cpu().pin_memory() for t in v] if isinstance(v, list) else v.cpu().pin_memory()) for k, v in d.items()}
+            for d in data[:2]]
+
+    def run(fr):
+        return pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts,
+                                          wl["iterations"], rng)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warm):
+        run(data[i % len(data)])
+    barrier()
+    l0 = _timing.LAUNCH_COUNT
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for fr in data:
+        run(fr)
+    e1.record()
+    barrier()
+    launches = _timing.LAUNCH_COUNT - l0
+    ms = e0.elapsed_time(e1)
+    # end to end: window inputs from pinned host memory, the final loss read back
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(len(data)):
+        h = host[i % len(host)]
+        fr = {k: ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v.to(dev, non_blocking=True))
+              for k, v in h.items() if k in ("target", "sources", "K")}
+        float(run(fr)["losses"][-1])
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    frames = wl["b"] * total_mbs
+    h2d = sum(t.numel() * 4 for t in [host[0]["target"], host[0]["K"]] + host[0]["sources"])
+    print(json.dumps({"metric": "PFT frames/s", "value": frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world,
+                      "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": wl["desc"], "window_minibatches_per_gpu": steps, "parallelism": "shard%d" % world,
+                                 "networks": "stand-in TinyDepthNet/TinyPoseNet (the reference nets are out of scope)",
+                                 "launch": "eager"},
+                      "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                              "d2h_bytes_per_step": 4},
+                      "gpu_launches": launches}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS) + sorted(PFT_WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=None, help="steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of replaying CUDA graphs")
     args = ap.parse_args()
+    if args.workload in PFT_WORKLOADS:
+        return main_pft(args)
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -121,6 +121,25 @@ int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
 int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
                         int B, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
 
+/* ---- the `return_errors` photometric block of solve_pose_iteratively (train_mono.py:84-92),
+ *      also compute_photometric_error (optimization_experiments/helpers.py:12-18) ----------
+ * For N stacked pairs: tgt / src are [N,3,H,W] views (channel slices of the 6-channel stack),
+ * rec [N,3,H,W], proj_depth / comp_depth [N,1,H,W] contiguous (the outputs of inverse_warp2).
+ *   auto_err  = mean_c(w_l1 * clamp|tgt - src| + w_ssim * SSIM(tgt, src))
+ *   diff      = mean_c(w_l1 * clamp|rec - tgt| + w_ssim * SSIM(tgt, rec))
+ *   auto_mask = diff < auto_err            weight = 1 - clamp(|cd - pd| / (cd + pd), 0, 1)
+ * coef [N,P,H,W], P = tcsfm_photo_coef_planes(), is the workspace the backward needs (NULL for
+ * inference).  The backward returns the gradients w.r.t. rec and the two depths. */
+int tcsfm_photo_coef_planes(void);
+int tcsfm_photo_fwd(const float* tgt, int64_t tgt_sb, int64_t tgt_sc, const float* src, int64_t src_sb, int64_t src_sc,
+                    const float* rec, const float* proj_depth, const float* comp_depth,
+                    float* auto_err, float* diff, float* auto_mask, float* weight, float* coef,
+                    int N, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
+int tcsfm_photo_bwd(const float* tgt, int64_t tgt_sb, int64_t tgt_sc, const float* rec,
+                    const float* proj_depth, const float* comp_depth, const float* coef,
+                    const float* g_diff, const float* g_weight, float* g_rec, float* g_pd, float* g_cd,
+                    int N, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
+
 /* ---- glue of Compute_Loss.forward (losses.py:75-140) ----------------------------
  * pose [N,6] (times `sign`; every call site passes -pose) -> K @ [Rx Ry Rz | t] as [N,12]
  * (models/stn.py:81-116,143-158,262); row i uses K[i % Bk].  Bit-identical to the eager

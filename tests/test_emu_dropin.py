@@ -188,3 +188,26 @@ def test_ssim_gradient_noise_floor(emu_ops):
     (losses.SSIM_Loss()(xx, y) * gout).sum().backward()
     assert rel_l2(xx.grad, r32) < rel_l2(r32, r64)
     assert rel_l2(xx.grad, r64) < 1.5 * rel_l2(r32, r64)
+
+
+def test_pft_driver_matches_oracle_backend(emu_ops):
+    """Two optimisation epochs of a PFT window with stand-in networks: fused path (emulated) vs
+    the oracle plugged into the same driver."""
+    from oracle import ref_torch as O
+    from tcsfm_b200 import pft_driver, synth
+
+    class OracleBackend:
+        solve_pose_iteratively = staticmethod(O.iterative_pose)
+        compute_optimization_loss = staticmethod(O.pft_window_loss)
+        disp_to_depth = staticmethod(O.disp_to_depth)
+
+    fr = synth.make_frames(2, 24, 40, seed=6)
+    depth_net, pose_net = synth.TinyDepthNet(seed=2), synth.TinyPoseNet(seed=2)
+    opts = {"epochs": 3}
+    got = pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts, iterations=2)
+    ref = pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts, iterations=2,
+                                     backend=OracleBackend)
+    assert torch.allclose(got["losses"], ref["losses"], rtol=1e-5, atol=0), (got["losses"], ref["losses"])
+    assert (got["disparity"] - ref["disparity"]).abs().max() < 1e-6
+    # the caller's network is untouched: every window starts from the same weights
+    assert all(torch.equal(a, b) for a, b in zip(depth_net.state_dict().values(), synth.TinyDepthNet(seed=2).state_dict().values()))

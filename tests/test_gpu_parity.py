@@ -252,3 +252,27 @@ def test_pose_proj_bit_exact_vs_eager_cuda():
         (K.repeat(n // bk, 1, 1) @ stn.pose_vec2mat(-p)).backward(gp)
         g_pose = _raw.pose_proj_bwd(_lib.lib(), pose, K, -1.0, gp)
         assert rel_l2(g_pose, p.grad) < 1e-5
+
+
+def test_pft_window_trajectory_vs_oracle():
+    """Four optimisation epochs of a PFT window (stand-in networks) through the fused path and
+    through the oracle on the same GPU: loss trajectory within 1e-4 (SURVEY.md §4 integration)."""
+    from tcsfm_b200 import pft_driver
+
+    class OracleBackend:
+        solve_pose_iteratively = staticmethod(O.iterative_pose)
+        compute_optimization_loss = staticmethod(
+            lambda opts, tgt, disp, init, fwd, inv: O.pft_window_loss(opts, tgt, disp, init, fwd, inv))
+        disp_to_depth = staticmethod(O.disp_to_depth)
+
+    b, h, w = 3, 96, 160
+    fr = frames(b, h, w, 0.01, synth.KITTI_DEPTH_RANGE, seed=8)
+    depth_net = synth.TinyDepthNet(seed=1).to(DEV)
+    pose_net = synth.TinyPoseNet(seed=1).to(DEV)
+    opts = {"epochs": 4}
+    got = pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts, iterations=3)
+    ref = pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts, iterations=3,
+                                     backend=OracleBackend)
+    assert got["losses"].shape == (4,)
+    assert torch.allclose(got["losses"], ref["losses"], rtol=1e-4, atol=0), (got["losses"], ref["losses"])
+    assert (got["disparity"] - ref["disparity"]).abs().max() < 1e-4

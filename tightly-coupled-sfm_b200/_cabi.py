@@ -48,6 +48,11 @@ SIGNATURES = {
                                       C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "tcsfm_pair_loss_bwd": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "tcsfm_photo_coef_planes": (C.c_int, []),
+    "tcsfm_photo_fwd": (C.c_int, [_fp, _i64, _i64, _fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                  C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "tcsfm_photo_bwd": (C.c_int, [_fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+                                  C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "tcsfm_pose_proj_fwd": (C.c_int, [_fp, C.c_float, _fp, C.c_int, _fp, C.c_int, C.c_void_p]),
     "tcsfm_pose_proj_bwd": (C.c_int, [_fp, C.c_float, _fp, C.c_int, _fp, _fp, C.c_int, C.c_void_p]),
     "tcsfm_min_reduce": (C.c_int, [_fp, _i64, C.c_int, _i64, _fp, C.c_void_p]),

@@ -276,3 +276,41 @@ def pair_loss_bwd_shared(lib, batch, mask, sums, coef, g_scalars, g_min, min_inf
     _cabi.check(lib, rc)
     _timing.count_launch()
     return g_proj
+
+
+# ---------------------------------------------------------------------------
+# photometric error maps of solve_pose_iteratively(return_errors=True) (csrc/photo_kernels.cu)
+# ---------------------------------------------------------------------------
+
+def photo_fwd(lib, tgt, src, rec, proj_depth, comp_depth, w_l1, w_ssim, flags=0, want_grad=True):
+    n, _, h, w = rec.shape
+    tgt, tsb, tsc = image_view(tgt, "tgt")
+    src, ssb, ssc = image_view(src, "src")
+    rec, pd, cd = _f32c(rec, "rec"), _f32c(proj_depth, "proj_depth"), _f32c(comp_depth, "comp_depth")
+    dev = rec.device
+    outs = [torch.empty((n, 1, h, w), dtype=torch.float32, device=dev) for _ in range(4)]
+    coef = torch.empty((n, lib.tcsfm_photo_coef_planes(), h, w), dtype=torch.float32, device=dev) if want_grad else None
+    with _timing.launch("photo_fwd", rec.is_cuda):
+        rc = lib.tcsfm_photo_fwd(_ptr(tgt), tsb, tsc, _ptr(src), ssb, ssc, _ptr(rec), _ptr(pd), _ptr(cd),
+                                 _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), _ptr(coef),
+                                 n, h, w, w_l1, w_ssim, flags, _stream(rec))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return outs[0], outs[1], outs[2], outs[3], coef
+
+
+def photo_bwd(lib, tgt, rec, proj_depth, comp_depth, coef, g_diff, g_weight, w_l1, w_ssim, flags=0):
+    n, _, h, w = rec.shape
+    tgt, tsb, tsc = image_view(tgt, "tgt")
+    rec, pd, cd = _f32c(rec, "rec"), _f32c(proj_depth, "proj_depth"), _f32c(comp_depth, "comp_depth")
+    g_diff, g_weight = _f32c(g_diff, "g_diff"), _f32c(g_weight, "g_weight")
+    dev = rec.device
+    g_rec = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+    g_pd = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+    g_cd = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+    with _timing.launch("photo_bwd", rec.is_cuda):
+        rc = lib.tcsfm_photo_bwd(_ptr(tgt), tsb, tsc, _ptr(rec), _ptr(pd), _ptr(cd), _ptr(coef), _ptr(g_diff), _ptr(g_weight),
+                                 _ptr(g_rec), _ptr(g_pd), _ptr(g_cd), n, h, w, w_l1, w_ssim, flags, _stream(rec))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return g_rec, g_pd, g_cd

@@ -208,3 +208,30 @@ class FrameLossFn(torch.autograd.Function):
                 meta["w_l1"], meta["w_ssim"], ctx.flags, need_ref)
             g_pose = _raw.pose_proj_bwd(lib(), poses, K, -1.0, g_proj.reshape(-1, 3, 4))
         return (None, None, None, g_pose) + (None,) * meta["n_img"] + tuple(g_depths[i] for i in range(ctx.n_dep))
+
+
+class PhotoErrorFn(torch.autograd.Function):
+    """(tgt, src, rec, projected_depth, computed_depth) -> (auto_mask_error, diff_img, auto_mask,
+    weight_mask) of train_mono.py:84-92 in one launch; backward w.r.t. rec and the depths in one."""
+
+    @staticmethod
+    def forward(ctx, tgt, src, rec, proj_depth, comp_depth, w_l1, w_ssim):
+        _require_cuda(tgt, src, rec, proj_depth, comp_depth)
+        want_grad = any(ctx.needs_input_grad[2:5])
+        with _guard(rec):
+            auto_err, diff, auto_mask, weight, coef = _raw.photo_fwd(lib(), tgt, src, rec, proj_depth, comp_depth,
+                                                                     w_l1, w_ssim, ARITH_FLAGS, want_grad)
+        if want_grad:
+            ctx.save_for_backward(tgt, rec, proj_depth, comp_depth, coef)
+            ctx.weights = (w_l1, w_ssim)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(auto_err, auto_mask)
+        return auto_err, diff, auto_mask, weight
+
+    @staticmethod
+    def backward(ctx, g_auto_err, g_diff, g_auto_mask, g_weight):
+        tgt, rec, proj_depth, comp_depth, coef = ctx.saved_tensors
+        with _guard(rec):
+            g_rec, g_pd, g_cd = _raw.photo_bwd(lib(), tgt, rec, proj_depth, comp_depth, coef, g_diff, g_weight,
+                                               ctx.weights[0], ctx.weights[1], ARITH_FLAGS)
+        return None, None, g_rec, g_pd, g_cd, None, None

@@ -6,6 +6,7 @@ Adam, plotting; optimizer.py:136-297) is the reference's harness and calls these
 """
 import torch
 
+from . import ops
 from .losses import SSIM_Loss, get_smooth_loss
 from .stn import inverse_warp2
 
@@ -52,14 +53,11 @@ def compute_optimization_loss(options, target_img, target_disparity, init_dispar
 
 
 def compute_photometric_error(target_img, source_img, target_depth, source_depth, pose, intrinsics):
-    """helpers.py:8-23: single-pair forward error maps for the loss-surface plots."""
-    ssim_loss = SSIM_Loss()
+    """helpers.py:8-23: single-pair forward error maps for the loss-surface plots (one warp
+    launch + one photometric launch)."""
     img_rec, valid_mask, projected_depth, computed_depth = inverse_warp2(
         source_img, target_depth, source_depth, -pose, intrinsics, 'zeros')
-    tgt = target_img.clone().detach()
-    diff_img = (0.15 * (img_rec - tgt).abs().clamp(0, 1) + 0.85 * ssim_loss(tgt, img_rec)).mean(1, True)
-    diff_depth = ((computed_depth - projected_depth).abs() / (computed_depth + projected_depth)).clamp(0, 1)
-    auto_mask = (0.15 * (source_img - tgt).abs().clamp(0, 1) + 0.85 * ssim_loss(tgt, source_img)).mean(1, True)
-    auto_mask = (diff_img < auto_mask).float()
+    _, diff_img, auto_mask, weight_mask = ops.PhotoErrorFn.apply(
+        target_img.detach(), source_img.detach(), img_rec, projected_depth, computed_depth, 0.15, 0.85)
     return {'diff_img': diff_img, 'img_rec': img_rec, 'valid_mask': auto_mask * valid_mask,
-            'weight_mask': 1 - diff_depth, 'poses': pose}
+            'weight_mask': weight_mask, 'poses': pose}

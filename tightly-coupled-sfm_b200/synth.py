@@ -84,3 +84,19 @@ class TinyPoseNet(torch.nn.Module):
         feat = imgs.mean(dim=(2, 3))                      # [N,6]
         sign = torch.sign(feat[:, 0:1] - feat[:, 3:4] + 1e-6).detach()
         return self.scale * torch.tanh(feat @ self.mix) + sign * 0 + self.base
+
+
+class TinyDepthNet(torch.nn.Module):
+    """Stand-in for the reference depth network (models/depth_models.py, out of scope):
+    `encoder` + `decoder` sub-modules like the reference's, input [N,3,H,W] -> list with the
+    scale-0 sigmoid disparity [N,1,H,W]."""
+
+    def __init__(self, seed=0, width=8):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.encoder = torch.nn.Sequential(torch.nn.Conv2d(3, width, 3, padding=1), torch.nn.ELU(),
+                                           torch.nn.Conv2d(width, width, 3, padding=1), torch.nn.ELU())
+        self.decoder = torch.nn.Conv2d(width, 1, 3, padding=1)
+
+    def forward(self, imgs):
+        return [torch.sigmoid(self.decoder(self.encoder(imgs)))]

@@ -41,17 +41,14 @@ def solve_disp(depth_model, target_img, source_img_list):
 
 
 def photometric_error_maps(imgs, img_rec, projected_depth, computed_depth, ssim_loss=None):
-    """The ``return_errors`` arithmetic of train_mono.py:84-92 for a stack of pairs.
-    imgs is the 6-channel [reconstruction target | source] stack.  Returns
+    """The ``return_errors`` arithmetic of train_mono.py:84-92 for a stack of pairs, as one
+    fused launch (csrc/photo_kernels.cu).  imgs is the 6-channel [reconstruction target |
+    source] stack (data: it carries no gradient in any reference call site).  Returns
     (auto_mask_error, diff_img, auto_mask, weight_mask)."""
-    ssim_loss = ssim_loss or SSIM_Loss()
-    tgt, src = imgs[:, 0:3], imgs[:, 3:6]
-    auto_mask_error = (0.15 * (tgt - src).abs().clamp(0, 1) + 0.85 * ssim_loss(tgt, src)).mean(1, True)
-    tgt_d = tgt.detach()
-    diff_img = (0.15 * (img_rec - tgt_d).abs().clamp(0, 1) + 0.85 * ssim_loss(tgt_d, img_rec)).mean(1, True)
-    auto_mask = (diff_img < auto_mask_error).float()
-    diff_depth = ((computed_depth - projected_depth).abs() / (computed_depth + projected_depth)).clamp(0, 1)
-    return auto_mask_error, diff_img, auto_mask, 1 - diff_depth
+    if imgs.requires_grad:
+        raise NotImplementedError("gradients w.r.t. the input images are not implemented "
+                                  "(no reference call site differentiates them)")
+    return ops.PhotoErrorFn.apply(imgs[:, 0:3], imgs[:, 3:6], img_rec, projected_depth, computed_depth, 0.15, 0.85)
 
 
 def solve_pose_iteratively(num_iter, depths, pose_model, target_img, source_img_list, intrinsics, return_errors=False):
