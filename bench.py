@@ -440,8 +440,12 @@ def main():
     roofline = None
     if dom:
         ach = bytes_per_launch[dom] / (ksum[dom]["avg_ms"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tpath) and args.workload == "kitti":
+            traffic = json.load(open(tpath)).get(dom)          # dram read+write per launch from the committed ncu capture
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": ksum[dom]["avg_ms"],
+                    "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": ksum[dom]["avg_ms"],
                     "algorithmic_bytes_per_launch": bytes_per_launch[dom],
                     "step_algorithmic_GBps": 84 * npx * pairs / (ms_total / args.steps * 1e-3) / 1e9,
                     "kernels": ksum}

@@ -32,7 +32,7 @@ namespace tcsfm {
 #define TCSFM_FWD_MIN_BLOCKS 4
 #endif
 #ifndef TCSFM_BWD_MIN_BLOCKS
-#define TCSFM_BWD_MIN_BLOCKS 2
+#define TCSFM_BWD_MIN_BLOCKS 4      // measured: 4 CTAs/SM with ~200 B of spills beats 2-3 CTAs/SM without (latency bound)
 #endif
 
 constexpr int kMaxGroups = 8;
@@ -361,20 +361,22 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             out[j] = s;
         }
     };
-    hsum(0, h[0]);
-    hsum(1, h[1]);
-#pragma unroll
+    hsum(0, h[1]);
+    hsum(1, h[2]);
+#pragma unroll 1
     for (int k = 0; k < kPixPerThread; ++k) {
-        hsum(k + 2, h[(k + 2) % 3]);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { h[0][j] = h[1][j]; h[1][j] = h[2][j]; }
+        hsum(k + 2, h[2]);
         const int gy = y0 + ty0 + k;
         if (gx < W && gy < H) {
             float V[9];
             const bool dup_u = (gy == 1), dup_d = (gy == H - 2);
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
-                float s = (h[k % 3][j] + h[(k + 1) % 3][j]) + h[(k + 2) % 3][j];
-                if (dup_u) s += h[k % 3][j];
-                if (dup_d) s += h[(k + 2) % 3][j];
+                float s = (h[0][j] + h[1][j]) + h[2][j];
+                if (dup_u) s += h[0][j];
+                if (dup_d) s += h[2][j];
                 V[j] = s;
             }
             const int pix = gy * W + gx;
