@@ -10,6 +10,7 @@ SSIM = 1 << 2
 DEPTH_MASK = 1 << 3
 DEPTH_CONSIST = 1 << 4
 SHARED_GRADS = 1 << 5
+ARITH_BMM_NOFMA = 1 << 6
 
 _fp = C.c_void_p          # device (or, in the emulator, host) pointer to float
 _i64 = C.c_int64

@@ -16,6 +16,15 @@ from ._lib import lib
 ARITH_FLAGS = 0
 
 
+def arith_flags(batch, height, width):
+    """Arithmetic flavour of a launch standing in for reference calls with `batch` pairs: eager
+    CUDA bmm uses a non-fused kernel for batch 1 and fewer than 2^18 pixels (include/tcsfm.h)."""
+    flags = ARITH_FLAGS
+    if not (flags & _cabi.ARITH_CPU) and batch == 1 and height * width < (1 << 18):
+        flags |= _cabi.ARITH_BMM_NOFMA
+    return flags
+
+
 def _guard(t):
     """Makes the tensor's GPU current for the launch (the C ABI launches on the
     current device / the stream it is handed)."""
@@ -37,7 +46,7 @@ class InverseWarp2Fn(torch.autograd.Function):
     def forward(ctx, img, depth, ref_depth, kinv, proj):
         _require_cuda(img, depth, ref_depth, kinv, proj)
         ctx.set_materialize_grads(False)
-        ctx.flags = ARITH_FLAGS
+        ctx.flags = arith_flags(img.shape[0], img.shape[2], img.shape[3])
         with _guard(img):
             out_img, valid, pd, cd = _raw.warp_fwd(lib(), img, depth, ref_depth, kinv, proj, ctx.flags)
         ctx.save_for_backward(img, depth, ref_depth, kinv, proj)
@@ -93,7 +102,7 @@ class PairLossFn(torch.autograd.Function):
             t = tensors[4 * i:4 * i + 4]
             groups.append({"tgt_img": t[0], "ref_img": t[1], "tgt_depth": t[2], "ref_depth": t[3],
                            "kinv": kinv, "proj": proj[i * b:(i + 1) * b]})
-        flags = flags | ARITH_FLAGS
+        flags = flags | arith_flags(b, tensors[0].shape[2], tensors[0].shape[3])
         with _guard(kinv):
             batch = _raw.PairBatch(groups)
             want_grad = any(ctx.needs_input_grad)
@@ -165,7 +174,7 @@ class FrameLossFn(torch.autograd.Function):
         images, depths = tensors[:meta["n_img"]], tensors[meta["n_img"]:]
         groups = meta["groups"]
         g, b = len(groups), K.shape[0]
-        flags = meta["flags"] | ARITH_FLAGS
+        flags = meta["flags"] | arith_flags(b, images[0].shape[2], images[0].shape[3])
         with _guard(K):
             kinv = kinv.contiguous()
             proj = _raw.pose_proj_fwd(lib(), poses, K, -1.0)
