@@ -278,9 +278,9 @@ def test_pft_window_trajectory_vs_oracle():
     assert (got["disparity"] - ref["disparity"]).abs().max() < 1e-4
 
 
-@pytest.mark.parametrize("hw", [(192, 640), (256, 320), (511, 513), (512, 512), (376, 1242)])
+@pytest.mark.parametrize("hw", [(192, 640), (256, 320), (344, 677), (511, 513), (512, 512), (376, 1242)])
 def test_batch_one_is_bit_exact_too(hw):
-    """With batch 1 eager PyTorch's k=3 bmm switches kernels below 2^18 pixels (no FMA); the
+    """With batch 1 eager PyTorch's k=3 bmm switches kernels at 9*H*W <= 2^21 (no FMA below); the
     operators pick the matching arithmetic so masks stay bit-exact and gradients tight."""
     h, w = hw
     fr = frames(1, h, w, 0.02, synth.KITTI_DEPTH_RANGE, seed=13)

@@ -18,9 +18,10 @@ ARITH_FLAGS = 0
 
 def arith_flags(batch, height, width):
     """Arithmetic flavour of a launch standing in for reference calls with `batch` pairs: eager
-    CUDA bmm uses a non-fused kernel for batch 1 and fewer than 2^18 pixels (include/tcsfm.h)."""
+    CUDA bmm runs a non-fused kernel for batch 1 while m*n*k = 9*H*W <= 2^21 (bisected on the
+    B200: last non-fused size 233016, tools/probe_bmm_b1_bisect.py; include/tcsfm.h)."""
     flags = ARITH_FLAGS
-    if not (flags & _cabi.ARITH_CPU) and batch == 1 and height * width < (1 << 18):
+    if not (flags & _cabi.ARITH_CPU) and batch == 1 and 9 * height * width <= (1 << 21):
         flags |= _cabi.ARITH_BMM_NOFMA
     return flags
 
