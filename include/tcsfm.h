@@ -154,6 +154,14 @@ int tcsfm_pose_proj_fwd(const float* pose, float sign, const float* K, int Bk, f
 int tcsfm_pose_proj_bwd(const float* pose, float sign, const float* K, int Bk, const float* g_proj,
                         float* g_pose, int N, void* stream);
 
+/* disp_to_depth (utils/learning_helpers.py:77-86) for `count` <= 4 maps of n floats in one launch:
+ * depth = 1 / (min_disp + range * disp), range = max_disp - min_disp; pointer tables are HOST
+ * arrays of device pointers.  Backward: g_disp = -g_depth * depth^2 * range. */
+int tcsfm_disp_to_depth_fwd(const float* const* disp, float* const* depth, int count, int64_t n,
+                            float min_disp, float range, void* stream);
+int tcsfm_disp_to_depth_bwd(const float* const* g_depth, const float* const* depth, float* const* g_disp, int count,
+                            int64_t n, float range, void* stream);
+
 /* out_sum[0] = sum_i min_j base[j*stride + i], j < count, i < n  (losses.py:129-131). */
 int tcsfm_min_reduce(const float* base, int64_t stride, int count, int64_t n, float* out_sum, void* stream);
 

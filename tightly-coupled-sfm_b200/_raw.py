@@ -314,3 +314,33 @@ def photo_bwd(lib, tgt, rec, proj_depth, comp_depth, coef, g_diff, g_weight, w_l
     _cabi.check(lib, rc)
     _timing.count_launch()
     return g_rec, g_pd, g_cd
+
+
+def _ptr_table(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def disp_to_depth_fwd(lib, disps, min_disp, disp_range):
+    """disps: list of <= 4 equally shaped fp32 maps -> list of depth maps (one launch)."""
+    disps = [_f32c(d, "disp") for d in disps]
+    depths = [torch.empty_like(d) for d in disps]
+    with _timing.launch("disp_to_depth_fwd", disps[0].is_cuda):
+        rc = lib.tcsfm_disp_to_depth_fwd(_ptr_table(disps), _ptr_table(depths), len(disps), disps[0].numel(),
+                                         min_disp, disp_range, _stream(disps[0]))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return depths
+
+
+def disp_to_depth_bwd(lib, g_depths, depths, disp_range):
+    g_depths = [_f32c(g, "g_depth") for g in g_depths]
+    g_disps = [torch.empty_like(d) for d in depths]
+    with _timing.launch("disp_to_depth_bwd", depths[0].is_cuda):
+        rc = lib.tcsfm_disp_to_depth_bwd(_ptr_table(g_depths), _ptr_table(depths), _ptr_table(g_disps), len(depths),
+                                         depths[0].numel(), disp_range, _stream(depths[0]))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return g_disps

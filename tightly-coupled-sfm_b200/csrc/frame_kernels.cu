@@ -118,6 +118,31 @@ __global__ void pose_proj_bwd_kernel(const float* __restrict__ pose, float sign,
     out[3] = sign * g_rx; out[4] = sign * g_ry; out[5] = sign * g_rz;
 }
 
+// disp_to_depth (utils/learning_helpers.py:77-86) for up to 4 equally sized maps in one launch:
+// depth = 1 / (min_disp + (max_disp - min_disp) * disp), each step rounded like the eager operators
+// (mul by scalar, add scalar, reciprocal).  Backward: g_disp = -g_depth * depth^2 * (max_disp - min_disp).
+struct MapPtrs { const float* in[4]; const float* aux[4]; float* out[4]; int count; };
+
+__global__ void __launch_bounds__(256)
+disp_to_depth_fwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float min_disp, float range) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < M.count; ++k) {
+        const float scaled = __fadd_rn(__fmul_rn(__ldg(M.in[k] + i), range), min_disp);
+        M.out[k][i] = __frcp_rn(scaled);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+disp_to_depth_bwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float range) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < M.count; ++k) {
+        const float d = __ldg(M.aux[k] + i);            // the depth computed by the forward
+        M.out[k][i] = -__ldg(M.in[k] + i) * d * d * range;
+    }
+}
+
 constexpr int kReduceThreads = 256;
 
 __global__ void __launch_bounds__(kReduceThreads)
@@ -177,6 +202,28 @@ extern "C" int tcsfm_pose_proj_bwd(const float* pose, float sign, const float* K
     if (!pose || !K || !g_proj || !g_pose || N <= 0 || Bk <= 0) { set_error("tcsfm_pose_proj_bwd: bad arguments"); return 1; }
     TCSFM_LAUNCH(pose_proj_bwd_kernel, dim3((N + 63) / 64), dim3(64), 0, stream, pose, sign, K, Bk, g_proj, g_pose, N);
     return check_launch("tcsfm_pose_proj_bwd");
+}
+
+extern "C" int tcsfm_disp_to_depth_fwd(const float* const* disp, float* const* depth, int count, int64_t n,
+                                       float min_disp, float range, void* stream) {
+    if (!disp || !depth || count < 1 || count > 4 || n <= 0) { set_error("tcsfm_disp_to_depth_fwd: bad arguments"); return 1; }
+    MapPtrs M;
+    memset(&M, 0, sizeof(M));
+    M.count = count;
+    for (int k = 0; k < count; ++k) { M.in[k] = disp[k]; M.out[k] = depth[k]; }
+    TCSFM_LAUNCH(disp_to_depth_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, M, n, min_disp, range);
+    return check_launch("tcsfm_disp_to_depth_fwd");
+}
+
+extern "C" int tcsfm_disp_to_depth_bwd(const float* const* g_depth, const float* const* depth, float* const* g_disp, int count,
+                                       int64_t n, float range, void* stream) {
+    if (!g_depth || !depth || !g_disp || count < 1 || count > 4 || n <= 0) { set_error("tcsfm_disp_to_depth_bwd: bad arguments"); return 1; }
+    MapPtrs M;
+    memset(&M, 0, sizeof(M));
+    M.count = count;
+    for (int k = 0; k < count; ++k) { M.in[k] = g_depth[k]; M.aux[k] = depth[k]; M.out[k] = g_disp[k]; }
+    TCSFM_LAUNCH(disp_to_depth_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, M, n, range);
+    return check_launch("tcsfm_disp_to_depth_bwd");
 }
 
 extern "C" int tcsfm_min_reduce(const float* base, int64_t stride, int count, int64_t n, float* out_sum, void* stream) {

@@ -477,7 +477,13 @@ extern "C" int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
         PairLaunch L;
         memset(&L, 0, sizeof(L));
         if (int rc = fill_launch(L, groups + base, n, B, H, W, w_l1, w_ssim, flags, "tcsfm_pair_loss_fwd", false)) return rc;
-        for (int i = 0; i < n; ++i) cudaMemsetAsync(L.g[i].sums, 0, 4 * sizeof(float), (cudaStream_t)stream);
+        // zero the accumulated sums; groups whose buffers are adjacent share one memset
+        for (int i = 0; i < n;) {
+            int j = i + 1;
+            while (j < n && L.g[j].sums == L.g[j - 1].sums + 4) ++j;
+            cudaMemsetAsync(L.g[i].sums, 0, (size_t)(j - i) * 4 * sizeof(float), (cudaStream_t)stream);
+            i = j;
+        }
         dim3 grid(tiles, B, n), block(kTileThreads);
         TCSFM_LAUNCH(pair_fwd_kernel, grid, block, smem, stream, L);
         if (int rc = check_launch("tcsfm_pair_loss_fwd")) return rc;
@@ -500,7 +506,13 @@ extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
                 set_error("tcsfm_pair_loss_bwd: group %d: inconsistent min-reprojection fields", base + i); return 1;
             }
             if (L.g[i].g_ref_depth && !(flags & TCSFM_SHARED_GRADS)) cudaMemsetAsync(L.g[i].g_ref_depth, 0, (size_t)B * H * W * sizeof(float), (cudaStream_t)stream);
-            if (L.g[i].g_proj) cudaMemsetAsync(L.g[i].g_proj, 0, (size_t)B * 12 * sizeof(float), (cudaStream_t)stream);
+        }
+        for (int i = 0; i < n;) {                     // adjacent g_proj buffers share one memset
+            if (!L.g[i].g_proj) { ++i; continue; }
+            int j = i + 1;
+            while (j < n && L.g[j].g_proj == L.g[j - 1].g_proj + (size_t)B * 12) ++j;
+            cudaMemsetAsync(L.g[i].g_proj, 0, (size_t)(j - i) * B * 12 * sizeof(float), (cudaStream_t)stream);
+            i = j;
         }
         dim3 grid(tiles, B, n), block(kTileThreads);
         TCSFM_LAUNCH(pair_bwd_kernel, grid, block, smem, stream, L);

@@ -123,10 +123,12 @@ class Compute_Loss(nn.modules.Module):
                 and all(s[0].shape == specs[0][0].shape and s[1].shape == specs[0][0].shape for s in specs))
 
     def _frame_terms(self, specs, roles, intrinsics):
-        """All pair evaluations of one scale plus the min-reprojection / mean-on-mask reductions
-        as one fused autograd node.  `specs` carry the un-negated poses.  Returns the [3]
-        tensor (l_reconstruct_inverse, l_reconstruct_forward, l_depth)."""
-        images, depths = [], []
+        """All pair evaluations of one scale plus disp_to_depth, the pose algebra and the
+        min-reprojection / mean-on-mask reductions as one fused autograd node.  `specs` are
+        (tgt_img, ref_img, tgt_disp, ref_disp, pose) with full-resolution disparities and the
+        un-negated poses.  Returns the [3] tensor (l_reconstruct_inverse, l_reconstruct_forward,
+        l_depth)."""
+        images, disps = [], []
 
         def index(lst, t):
             for i, u in enumerate(lst):
@@ -135,16 +137,17 @@ class Compute_Loss(nn.modules.Module):
             lst.append(t)
             return len(lst) - 1
         groups = []
-        for role, (tgt_img, ref_img, tgt_depth, ref_depth, _) in zip(roles, specs):
+        for role, (tgt_img, ref_img, tgt_disp, ref_disp, _) in zip(roles, specs):
             groups.append((0 if role == 'inv' else 1, index(images, tgt_img), index(images, ref_img),
-                           index(depths, tgt_depth), index(depths, ref_depth)))
+                           index(disps, tgt_disp), index(disps, ref_disp)))
         want_depth = self.config['l_depth_consist'] == True          # noqa: E712
         meta = {"w_l1": float(self.config['l1_weight']), "w_ssim": float(self.config['l_ssim_weight']),
                 "flags": _pair_flags(self.config), "w_inverse": 0.3,
                 "w_depth": float(self.l_depth_consist_weight) if want_depth else 0.0,
+                "min_depth": self.config['min_depth'], "max_depth": self.config['max_depth'],
                 "n_img": len(images), "groups": groups}
-        poses = torch.cat([s[4][:, 0:6] for s in specs], 0)
-        return ops.FrameLossFn.apply(meta, inverse_intrinsics(intrinsics), intrinsics, poses, *images, *depths)
+        return ops.FrameLossFn.apply(meta, inverse_intrinsics(intrinsics), intrinsics,
+                                     *[s[4] for s in specs], *images, *disps)
 
     def forward(self, source_imgs, target_img, poses, disparity, intrinsics, pose_vec_weight=None,
                 validate=False, epoch=5, target_img_right=None):
@@ -160,32 +163,36 @@ class Compute_Loss(nn.modules.Module):
         for scale, disp in enumerate(disparity):
             if scale != 0:
                 disp = nn.functional.interpolate(disp, (h, w), mode='nearest')
-            _, d = disp_to_depth(disp, cfg['min_depth'], cfg['max_depth'])
             if cfg['l_smooth']:
                 losses['l_smooth'] += (self.l_smooth_weight * get_smooth_loss(disp, target_img)) / (2 ** scale)
             if cfg['l_reconstruction']:
+                # (tgt_img, ref_img, tgt_disp, ref_disp, pose); the pose handed to the warp is the
+                # negated prediction (losses.py:112,119) -- negated inside the fused node
                 specs, roles = [], []
                 for j, source_img in enumerate(source_imgs):
                     source_disparity = source_disparities[j][scale]
                     if scale != 0:
                         source_disparity = nn.functional.interpolate(source_disparity, (h, w), mode='nearest')
-                    _, source_d = disp_to_depth(source_disparity, cfg['min_depth'], cfg['max_depth'])
                     if cfg['l_smooth']:
                         losses['l_smooth'] += (self.l_smooth_weight * get_smooth_loss(source_disparity, source_img)) / (2 ** scale)
-                    # the pose handed to the warp is the negated prediction (losses.py:112,119)
                     if cfg['l_inverse']:   # inverse reconstruction: target reprojected into the source frame
-                        specs.append((source_img, target_img, source_d, d, poses_inv[j]))
+                        specs.append((source_img, target_img, source_disparity, disp, poses_inv[j]))
                         roles.append('inv')
-                    specs.append((target_img, source_img, d, source_d, poses[j]))
+                    specs.append((target_img, source_img, disp, source_disparity, poses[j]))
                     roles.append('fwd')
-                if not self._can_fuse_frame(specs, intrinsics):
-                    specs = [s_[:4] + (-s_[4],) for s_ in specs]
                 if self._can_fuse_frame(specs, intrinsics):
                     terms = self._frame_terms(specs, roles, intrinsics)
-                    losses['l_reconstruct_inverse'] += terms[0:1]
-                    losses['l_reconstruct_forward'] += terms[1:2]
-                    losses['l_depth'] += terms[2:3]
+                    fresh = scale == 0          # 0 + x == x: skip the add into the zero tensor
+                    for i, key in enumerate(('l_reconstruct_inverse', 'l_reconstruct_forward', 'l_depth')):
+                        losses[key] = terms[i:i + 1] if fresh else losses[key] + terms[i:i + 1]
                     continue
+                depth_of = {}
+
+                def to_depth(dmap):
+                    if id(dmap) not in depth_of:
+                        depth_of[id(dmap)] = disp_to_depth(dmap, cfg['min_depth'], cfg['max_depth'])[1]
+                    return depth_of[id(dmap)]
+                specs = [(s_[0], s_[1], to_depth(s_[2]), to_depth(s_[3]), -s_[4]) for s_ in specs]
                 results = self._pair_groups(specs, intrinsics)
                 reconstruction_errors = []
                 for role, (l_reprojection, l_depth, diff_img, _) in zip(roles, results):
@@ -200,8 +207,9 @@ class Compute_Loss(nn.modules.Module):
                 losses['l_reconstruct_forward'] += reconstruction_errors.mean()
         losses['total'] = 0
         for key in ('l_reconstruct_inverse', 'l_reconstruct_forward', 'l_depth', 'l_smooth'):
-            losses[key] = losses[key] / (self.num_scales)
-            losses['total'] += losses[key]
+            if self.num_scales != 1:               # x / 1 == x
+                losses[key] = losses[key] / (self.num_scales)
+            losses['total'] = losses[key] if isinstance(losses['total'], int) else losses['total'] + losses[key]
         return losses
 
     def mean_on_mask(self, diff, valid_mask):

@@ -160,24 +160,31 @@ class PoseProjFn(torch.autograd.Function):
 
 
 class FrameLossFn(torch.autograd.Function):
-    """The reconstruction terms of one scale of Compute_Loss.forward (losses.py:99-132) as
-    five launches forward (pose->K[R|t], pair kernel, min-reduce, finalize + memsets) and four
-    backward (prepare, pair kernel, pose chain rule + memsets).
+    """The reconstruction terms of one scale of Compute_Loss.forward (losses.py:86-132) as one
+    autograd node: disp_to_depth, pose -> K[R|t], the pair kernel over all direction/source
+    groups, min-reprojection reduce and the mean-on-mask finalize forward; prepare, the pair
+    kernel, the pose chain rule and the depth -> disparity chain rule backward.
 
-    apply(meta, kinv, K, poses [G*B,6], *images, *depths) -> [3] =
-    (l_reconstruct_inverse, l_reconstruct_forward, l_depth) before the division by num_scales.
-    meta: dict(w_l1, w_ssim, flags, w_inverse, w_depth, n_img, groups=[(role, tgt_img, ref_img,
-    tgt_depth, ref_depth)]) with indices into `images` / `depths`; role 0 = inverse, 1 = forward."""
+    apply(meta, kinv, K, *poses, *images, *disps) -> [3] = (l_reconstruct_inverse,
+    l_reconstruct_forward, l_depth) before the division by num_scales.
+    meta: dict(w_l1, w_ssim, flags, w_inverse, w_depth, min_depth, max_depth, n_img,
+    groups=[(role, tgt_img, ref_img, tgt_disp, ref_disp)]) with indices into `images` /
+    `disps`; one pose [B,6] per group (un-negated); role 0 = inverse, 1 = forward."""
 
     @staticmethod
-    def forward(ctx, meta, kinv, K, poses, *tensors):
-        _require_cuda(kinv, K, poses, *tensors)
-        images, depths = tensors[:meta["n_img"]], tensors[meta["n_img"]:]
+    def forward(ctx, meta, kinv, K, *tensors):
+        _require_cuda(kinv, K, *tensors)
         groups = meta["groups"]
         g, b = len(groups), K.shape[0]
+        poses_in, images, disps = tensors[:g], tensors[g:g + meta["n_img"]], tensors[g + meta["n_img"]:]
         flags = meta["flags"] | arith_flags(b, images[0].shape[2], images[0].shape[3])
+        min_disp, max_disp = 1 / meta["max_depth"], 1 / meta["min_depth"]      # learning_helpers.py:82-83
         with _guard(K):
             kinv = kinv.contiguous()
+            depths = []
+            for i in range(0, len(disps), 4):
+                depths += _raw.disp_to_depth_fwd(lib(), disps[i:i + 4], min_disp, max_disp - min_disp)
+            poses = torch.cat([p[:, 0:6] for p in poses_in], 0)
             proj = _raw.pose_proj_fwd(lib(), poses, K, -1.0)
             specs = [{"tgt_img": images[ti], "ref_img": images[ri], "tgt_depth": depths[td], "ref_depth": depths[rd],
                       "kinv": kinv, "proj": proj[i * b:(i + 1) * b]} for i, (_, ti, ri, td, rd) in enumerate(groups)]
@@ -195,29 +202,36 @@ class FrameLossFn(torch.autograd.Function):
             cfg = _raw.make_frame_cfg([grp[0] for grp in groups], meta["w_inverse"], meta["w_depth"], n_px)
             out = _raw.frame_finalize(lib(), sums, min_sum, cfg)
         if want_grad:
-            ctx.save_for_backward(mask, sums, coef, diff, poses, K)
+            ctx.save_for_backward(mask, sums, coef, diff, poses, K, *depths)
             ctx.batch, ctx.cfg, ctx.meta, ctx.flags = batch, cfg, meta, flags
             ctx.min_info = (fwd_idx, step * n_px)
-            ctx.n_dep, ctx.dep_shape = len(depths), depths[0].shape
+            ctx.disp_range = max_disp - min_disp
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        mask, sums, coef, diff, poses, K = ctx.saved_tensors
+        mask, sums, coef, diff, poses, K = ctx.saved_tensors[:6]
+        depths = list(ctx.saved_tensors[6:])
         meta, groups = ctx.meta, ctx.meta["groups"]
+        g, b = len(groups), K.shape[0]
         fwd_idx, stride = ctx.min_info
         need_ref = (ctx.flags & (_cabi.DEPTH_MASK | _cabi.DEPTH_CONSIST)) != 0
         with _guard(K):
             g_scalars, g_min = _raw.frame_bwd_prepare(lib(), g_out, ctx.cfg)
-            g_depths = torch.empty((ctx.n_dep,) + tuple(ctx.dep_shape), dtype=torch.float32, device=K.device)
-            min_pos = [fwd_idx.index(i) if i in fwd_idx else -1 for i in range(len(groups))]
+            g_depths = torch.empty((len(depths),) + tuple(depths[0].shape), dtype=torch.float32, device=K.device)
+            min_pos = [fwd_idx.index(i) if i in fwd_idx else -1 for i in range(g)]
             min_first = diff[fwd_idx[0]] if fwd_idx else None
             g_proj = _raw.pair_loss_bwd_shared(
                 lib(), ctx.batch, mask, sums, coef, g_scalars, g_min, (min_first, stride, min_pos, len(fwd_idx)),
                 g_depths, [grp[3] for grp in groups], [grp[4] for grp in groups],
                 meta["w_l1"], meta["w_ssim"], ctx.flags, need_ref)
             g_pose = _raw.pose_proj_bwd(lib(), poses, K, -1.0, g_proj.reshape(-1, 3, 4))
-        return (None, None, None, g_pose) + (None,) * meta["n_img"] + tuple(g_depths[i] for i in range(ctx.n_dep))
+            g_disps = []
+            for i in range(0, len(depths), 4):
+                g_disps += _raw.disp_to_depth_bwd(lib(), [g_depths[j] for j in range(i, min(i + 4, len(depths)))],
+                                                  depths[i:i + 4], ctx.disp_range)
+        g_poses = tuple(g_pose[i * b:(i + 1) * b] for i in range(g))
+        return (None, None, None) + g_poses + (None,) * meta["n_img"] + tuple(g_disps)
 
 
 class PhotoErrorFn(torch.autograd.Function):
