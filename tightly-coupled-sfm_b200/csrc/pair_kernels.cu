@@ -101,10 +101,11 @@ __device__ __forceinline__ float blend(const Taps& v, const TapIdx& t) {
 }
 
 // Fills one shared-memory cell with (target, warped source) of the image pixel (rx, ry).
+template <int F>
 __device__ __forceinline__ void fill_cell(const PairCtx& c, const Cam& cam, const Arith& A, int rx, int ry,
                                           float2* tw, int cells, int cell, WarpPt& p, TapIdx& ti) {
     const int pix = ry * A.W + rx;
-    warp_point(cam, A, rx, ry, __ldg(c.tdep + pix), p);
+    warp_point<F>(cam, A, rx, ry, __ldg(c.tdep + pix), p);
     ti = make_taps(p, A.H, A.W);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
@@ -127,6 +128,7 @@ __device__ __forceinline__ void ring_cell(int r, int& cx, int& cy) {
     else { cx = kTileW; cy = r - 2 * (kTileW + 2) - kTileH; }
 }
 
+template <int F>
 __global__ void __launch_bounds__(kTileThreads, TCSFM_FWD_MIN_BLOCKS)
 pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
     using T1 = Tile<1>;
@@ -159,8 +161,13 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
         float m = 0.f, dd = 0.f;
         WarpPt p;
         TapIdx ti;
-        if (gx < W && gy < H) {
-            fill_cell(c, cam, A, gx, gy, tw, T1::kCells, cell, p, ti);
+        // cells of a partial tile that lie outside the image hold the reflected pixel (or zero)
+        const bool own = gx < W && gy < H;
+        int rx = gx, ry = gy;
+        const bool ok = own || T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx);
+        if (ok) fill_cell<F>(c, cam, A, rx, ry, tw, T1::kCells, cell, p, ti);
+        else zero_cell(tw, T1::kCells, cell);
+        if (own) {
             m = p.valid ? 1.f : 0.f;
             if (auto_mask) {
                 const int pix = gy * W + gx;
@@ -171,13 +178,9 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
                     l1[ch] = clamp01_nan(fabsf(__fsub_rn(v.x, v.y)));
                     ar[ch] = fabsf(__fsub_rn(v.x, __ldg(c.ref + ch * c.ref_sc + pix)));
                 }
-                if (!(mean3(l1[0], l1[1], l1[2], A) < mean3(ar[0], ar[1], ar[2], A))) m = 0.f;
+                if (!(mean3<F>(l1[0], l1[1], l1[2], A) < mean3<F>(ar[0], ar[1], ar[2], A))) m = 0.f;
             }
             if (need_depth) dd = depth_inconsistency(p.Z, blend(load_taps(c.rdep, ti, W), ti));
-        } else {
-            int ry, rx;
-            if (T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx)) fill_cell(c, cam, A, rx, ry, tw, T1::kCells, cell, p, ti);
-            else zero_cell(tw, T1::kCells, cell);
         }
         own_mask[k] = m;
         own_dd[k] = dd;
@@ -189,7 +192,7 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
         const int cell = T1::cell(cx, cy);
         WarpPt p;
         TapIdx ti;
-        if (T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx)) fill_cell(c, cam, A, rx, ry, tw, T1::kCells, cell, p, ti);
+        if (T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx)) fill_cell<F>(c, cam, A, rx, ry, tw, T1::kCells, cell, p, ti);
         else zero_cell(tw, T1::kCells, cell);
     }
     __syncthreads();
@@ -241,7 +244,7 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
         const int gy = y0 + ty0 + k;
         if (gx < W && gy < H) {
             const float s = esum[k];
-            const float diff0 = A.cpu_flavour ? div3_exact(s) : __fmul_rn(s, A.third);
+            const float diff0 = mean3_of_sum<F>(s, A);
             float diff = diff0;
             if (depth_mask) diff = __fmul_rn(diff0, __fsub_rn(1.0f, own_dd[k]));
             const int64_t o = (int64_t)b * n + gy * W + gx;
@@ -296,6 +299,7 @@ __device__ __forceinline__ float upstream_diff(const tcsfm_pair_group& g, const 
     return Gd;
 }
 
+template <int F>
 __global__ void __launch_bounds__(kTileThreads, TCSFM_BWD_MIN_BLOCKS)
 pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     using T1 = Tile<1>;
@@ -381,7 +385,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             }
             const int pix = gy * W + gx;
             WarpPt p;
-            warp_point(cam, A, gx, gy, __ldg(c.tdep + pix), p);
+            warp_point<F>(cam, A, gx, gy, __ldg(c.tdep + pix), p);
             const TapIdx ti = make_taps(p, H, W);
             const float m = __ldg(mask + pix);
             const float Gd = upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, m);
@@ -485,7 +489,7 @@ extern "C" int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
             i = j;
         }
         dim3 grid(tiles, B, n), block(kTileThreads);
-        TCSFM_LAUNCH(pair_fwd_kernel, grid, block, smem, stream, L);
+        TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(pair_fwd_kernel<F>, grid, block, smem, stream, L));
         if (int rc = check_launch("tcsfm_pair_loss_fwd")) return rc;
     }
     return 0;
@@ -515,7 +519,7 @@ extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
             i = j;
         }
         dim3 grid(tiles, B, n), block(kTileThreads);
-        TCSFM_LAUNCH(pair_bwd_kernel, grid, block, smem, stream, L);
+        TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(pair_bwd_kernel<F>, grid, block, smem, stream, L));
         if (int rc = check_launch("tcsfm_pair_loss_bwd")) return rc;
     }
     return 0;

@@ -67,6 +67,7 @@ __device__ __forceinline__ void strip_channel(const float2* plane, int tx, int t
     }
 }
 
+template <int F>
 __global__ void __launch_bounds__(kTileThreads, 3)
 photo_fwd_kernel(const __grid_constant__ PhotoArgs P) {
     using T1 = Tile<1>;
@@ -108,8 +109,8 @@ photo_fwd_kernel(const __grid_constant__ PhotoArgs P) {
         const int gy = gy0 + k;
         if (gx < W && gy < H) {
             const int64_t o = (int64_t)b * n + gy * W + gx;
-            const float diff = A.cpu_flavour ? div3_exact(e_rec[k]) : __fmul_rn(e_rec[k], A.third);
-            const float aerr = A.cpu_flavour ? div3_exact(e_src[k]) : __fmul_rn(e_src[k], A.third);
+            const float diff = mean3_of_sum<F>(e_rec[k], A);
+            const float aerr = mean3_of_sum<F>(e_src[k], A);
             if (P.diff) P.diff[o] = diff;
             if (P.auto_err) P.auto_err[o] = aerr;
             if (P.auto_mask) P.auto_mask[o] = (diff < aerr) ? 1.f : 0.f;
@@ -229,11 +230,12 @@ extern "C" int tcsfm_photo_fwd(const float* tgt, int64_t tgt_sb, int64_t tgt_sc,
     if (!src) { set_error("tcsfm_photo_fwd: null src"); return 1; }
     const size_t smem = 6 * Tile<1>::kCells * sizeof(float2);
 #ifndef TCSFM_HOST_EMU
-    cudaError_t e = cudaFuncSetAttribute(photo_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaSuccess;
+    TCSFM_DISPATCH_FLAVOUR(flags, e = cudaFuncSetAttribute(photo_fwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (e != cudaSuccess) { set_error("tcsfm_photo_fwd: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return 2; }
 #endif
     dim3 grid(((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH), N), block(kTileThreads);
-    TCSFM_LAUNCH(photo_fwd_kernel, grid, block, smem, stream, P);
+    TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(photo_fwd_kernel<F>, grid, block, smem, stream, P));
     return check_launch("tcsfm_photo_fwd");
 }
 

@@ -11,6 +11,7 @@ namespace tcsfm {
 
 constexpr int kWarpThreads = 256;
 
+template <int F>
 __global__ void __launch_bounds__(kWarpThreads)
 warp_fwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
                 const float* __restrict__ depth, const float* __restrict__ ref_depth,
@@ -25,7 +26,7 @@ warp_fwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
     const int v = pix / A.W, u = pix - v * A.W;
     const int64_t o = (int64_t)b * n + pix;
     WarpPt p;
-    warp_point(c, A, u, v, __ldg(depth + o), p);
+    warp_point<F>(c, A, u, v, __ldg(depth + o), p);
     if (out_img) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch)
@@ -46,6 +47,7 @@ __device__ __forceinline__ void scatter_taps(float* __restrict__ plane, const Wa
     if (y1in && x1in) atomicAdd(r0 + W + 1, g * (p.wx1 * p.wy1));
 }
 
+template <int F>
 __global__ void __launch_bounds__(kWarpThreads)
 warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
                 const float* __restrict__ depth, const float* __restrict__ ref_depth,
@@ -65,7 +67,7 @@ warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
         const int v = pix / A.W, u = pix - v * A.W;
         const int64_t o = (int64_t)b * n + pix;
         WarpPt p;
-        warp_point(c, A, u, v, __ldg(depth + o), p);
+        warp_point<F>(c, A, u, v, __ldg(depth + o), p);
         float g_ix = 0.f, g_iy = 0.f;
         if (g_oimg) {
 #pragma unroll
@@ -112,8 +114,8 @@ extern "C" int tcsfm_warp_fwd(const float* img, int64_t img_sb, int64_t img_sc,
     if (B > 65535) { set_error("tcsfm_warp_fwd: B=%d exceeds 65535", B); return 1; }
     const Arith A = make_arith(H, W, flags);
     dim3 grid((H * W + kWarpThreads - 1) / kWarpThreads, B), block(kWarpThreads);
-    TCSFM_LAUNCH(warp_fwd_kernel, grid, block, 0, stream, img, img_sb, img_sc, depth, ref_depth, kinv, proj,
-                 out_img, out_valid, out_proj_depth, out_comp_depth, A);
+    TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(warp_fwd_kernel<F>, grid, block, 0, stream, img, img_sb, img_sc, depth,
+                                               ref_depth, kinv, proj, out_img, out_valid, out_proj_depth, out_comp_depth, A));
     return check_launch("tcsfm_warp_fwd");
 }
 
@@ -132,7 +134,8 @@ extern "C" int tcsfm_warp_bwd(const float* img, int64_t img_sb, int64_t img_sc,
     if (g_proj) cudaMemsetAsync(g_proj, 0, (size_t)B * 12 * sizeof(float), (cudaStream_t)stream);
     if (g_img) cudaMemsetAsync(g_img, 0, 3 * plane, (cudaStream_t)stream);
     dim3 grid((H * W + kWarpThreads - 1) / kWarpThreads, B), block(kWarpThreads);
-    TCSFM_LAUNCH(warp_bwd_kernel, grid, block, 0, stream, img, img_sb, img_sc, depth, ref_depth, kinv, proj,
-                 g_out_img, g_out_proj_depth, g_out_comp_depth, g_depth, g_ref_depth, g_proj, g_img, A);
+    TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(warp_bwd_kernel<F>, grid, block, 0, stream, img, img_sb, img_sc, depth,
+                                               ref_depth, kinv, proj, g_out_img, g_out_proj_depth, g_out_comp_depth,
+                                               g_depth, g_ref_depth, g_proj, g_img, A));
     return check_launch("tcsfm_warp_bwd");
 }
