@@ -29,7 +29,7 @@ namespace tcsfm {
 
 // resident CTAs per SM the register allocation targets (256 threads each)
 #ifndef TCSFM_FWD_MIN_BLOCKS
-#define TCSFM_FWD_MIN_BLOCKS 4
+#define TCSFM_FWD_MIN_BLOCKS 3
 #endif
 #ifndef TCSFM_BWD_MIN_BLOCKS
 #define TCSFM_BWD_MIN_BLOCKS 4      // measured: 4 CTAs/SM with ~200 B of spills beats 2-3 CTAs/SM without (latency bound)
