@@ -30,6 +30,14 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout must carry exactly one JSON line, but NCCL writes its version banner to fd 1: park the
+# real stdout and route everything else that lands on fd 1 to stderr
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line_dict):
+    os.write(_REAL_STDOUT, (json.dumps(line_dict) + "\n").encode())
 
 PFT_WORKLOADS = {
     # sequential per-frame test-time optimisation (configs 3/4 of BASELINE.json); stand-in networks
@@ -175,7 +183,7 @@ def main_pft(args):
         pft_driver.optimize_window(dn, pn, fr["target"], fr["sources"], fr["K"], cpu_opts, wl["iterations"], rng, OracleBackend)
         dt = (time.perf_counter() - t0) * wl["epochs"] / cpu_opts["epochs"]
         fps = wl["b"] / dt
-        print(json.dumps({"impl": "reference", "metric": "PFT frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        emit(({"impl": "reference", "metric": "PFT frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                           "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"]},
                           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -240,7 +248,7 @@ def main_pft(args):
         return
     frames = wl["b"] * total_mbs
     h2d = sum(t.numel() * 4 for t in [host[0]["target"], host[0]["K"]] + host[0]["sources"])
-    print(json.dumps({"metric": "PFT frames/s", "value": frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world,
+    emit(({"metric": "PFT frames/s", "value": frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world,
                       "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": wl["desc"], "window_minibatches_per_gpu": steps, "parallelism": "shard%d" % world,
@@ -287,7 +295,7 @@ def main():
                                  "sample": "%d steps of the same B=%d minibatch, oracle port of the reference's "
                                            "PyTorch CPU path, torch threads=%d" % (steps, wl["b"], cores)},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     if not torch.cuda.is_available():
@@ -463,7 +471,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
