@@ -134,6 +134,14 @@ static inline float __int2float_rn(int x) { return (float)x; }
 static inline float __int_as_float(int x) { float f; std::memcpy(&f, &x, 4); return f; }
 static inline int __float_as_int(float f) { int x; std::memcpy(&x, &f, 4); return x; }
 
+// cp.async (cuda_pipeline.h primitives): a plain copy with trailing zero fill on the host
+static inline void __pipeline_memcpy_async(void* dst, const void* src, size_t size, size_t zfill = 0) {
+    std::memcpy(dst, src, size - zfill);
+    std::memset((char*)dst + (size - zfill), 0, zfill);
+}
+static inline void __pipeline_commit() {}
+static inline void __pipeline_wait_prior(int) {}
+
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }

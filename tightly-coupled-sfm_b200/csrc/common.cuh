@@ -13,6 +13,7 @@
     emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #else
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>

@@ -327,20 +327,23 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     const int ty0 = (threadIdx.x >> 6) * kPixPerThread;
     const int gx = x0 + tx;
 
-    // ---- phase B: coefficients of the tile + 1 ring, scaled by the upstream gradient of
-    //      diff_img at their pixel q (zero outside the image) ----
+    // ---- phase B: the nine coefficient planes of the tile + 1 ring go global -> shared with
+    //      cp.async (no register staging, all loads in flight at once; zero fill outside the
+    //      image), next to the upstream gradient of diff_img at each ring pixel ----
+    float* Gs = cs + 9 * T1::kCells;               // [cells] upstream gradient (0 outside the image)
     for (int cell = threadIdx.x; cell < T1::kCells; cell += kTileThreads) {
         int cx, cy;
         T1::cell_xy(cell, cx, cy);
         const int qx = x0 + cx, qy = y0 + cy;
-        float Gd = 0.f;
         const bool inside = qx >= 0 && qx < W && qy >= 0 && qy < H;
-        const int pix = qy * W + qx;
-        if (inside) Gd = upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, __ldg(mask + pix));
+        const int pix = inside ? qy * W + qx : 0;
 #pragma unroll
         for (int j = 0; j < 9; ++j)
-            cs[j * T1::kCells + cell] = inside ? Gd * __ldg(coef + (int64_t)j * n + pix) : 0.f;
+            __pipeline_memcpy_async(cs + j * T1::kCells + cell, coef + (int64_t)j * n + pix, 4, inside ? 0 : 4);
+        Gs[cell] = inside ? upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, __ldg(mask + pix)) : 0.f;
     }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
     __syncthreads();
 
     // ---- phases C + D, one own pixel at a time down the strip.
@@ -355,14 +358,12 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     const bool dup_l = (gx == 1), dup_r = (gx == W - 2);
     auto hsum = [&](int r, float (&out)[9]) {          // horizontal 3-sums of tile row ty0 - 1 + r
         const int c1 = T1::cell(tx, ty0 - 1 + r);
+        // upstream of the three neighbours; a border neighbour that is folded back counts twice
+        const float gl = Gs[c1 - 1] * (dup_l ? 2.f : 1.f), gm = Gs[c1], gr = Gs[c1 + 1] * (dup_r ? 2.f : 1.f);
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             const float* pl = cs + j * T1::kCells + c1;
-            const float l = pl[-1], m = pl[0], rr = pl[1];
-            float s = (l + m) + rr;
-            if (dup_l) s += l;
-            if (dup_r) s += rr;
-            out[j] = s;
+            out[j] = pl[-1] * gl + pl[0] * gm + pl[1] * gr;
         }
     };
     hsum(0, h[1]);
@@ -388,7 +389,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             warp_point<F>(cam, A, gx, gy, __ldg(c.tdep + pix), p);
             const TapIdx ti = make_taps(p, H, W);
             const float m = __ldg(mask + pix);
-            const float Gd = upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, m);
+            const float Gd = Gs[T1::cell(tx, ty0 + k)];
             float pd = 0.f, dd = 0.f;
             Taps td;
             if (need_depth) {
@@ -498,7 +499,7 @@ extern "C" int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
 extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
                                    float w_l1, float w_ssim, int flags, void* stream) {
     if (!groups || n_groups <= 0) { set_error("tcsfm_pair_loss_bwd: no groups"); return 1; }
-    const size_t smem = 9 * Tile<1>::kCells * sizeof(float);
+    const size_t smem = 10 * Tile<1>::kCells * sizeof(float);
     const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
     for (int base = 0; base < n_groups; base += kMaxGroups) {
         const int n = (n_groups - base < kMaxGroups) ? n_groups - base : kMaxGroups;
