@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 3
+#define TCSFM_ABI_VERSION 4
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -66,7 +66,11 @@ int tcsfm_warp_fwd(const float* img, int64_t img_sb, int64_t img_sc,
                    const float* depth, const float* ref_depth,
                    const float* kinv, const float* proj,
                    float* out_img, float* out_valid, float* out_proj_depth, float* out_comp_depth,
+                   const float* tgt, int64_t tgt_sb, int64_t tgt_sc, float* out_stack,
                    int B, int H, int W, int flags, void* stream);
+/* Optional fused glue of solve_pose_iteratively (train_mono.py:74-76,102-104): when `out_stack`
+ * [B,6,H,W] is given, the kernel also writes the next pose-network input
+ * [ tgt * valid_mask | projected_img ] (tgt is the [B,3,H,W] view of the reconstruction target). */
 
 /* Backward of the above (the autograd replay of stn.py:257-271).  g_out_* are the
  * upstream gradients (NULL = zero).  g_depth is overwritten; g_ref_depth [B,1,H,W],
@@ -76,8 +80,11 @@ int tcsfm_warp_bwd(const float* img, int64_t img_sb, int64_t img_sc,
                    const float* depth, const float* ref_depth,
                    const float* kinv, const float* proj,
                    const float* g_out_img, const float* g_out_proj_depth, const float* g_out_comp_depth,
+                   const float* g_out_stack,
                    float* g_depth, float* g_ref_depth, float* g_proj, float* g_img,
                    int B, int H, int W, int flags, void* stream);
+/* g_out_stack [B,6,H,W] (NULL = none): upstream gradient of `out_stack`; its channels 3:6 add to
+ * g_out_img. */
 
 /* ---- SSIM_Loss.forward (losses.py:27-41) and its backward ---------------------
  * x, y, out, g_out, g_x, g_y are contiguous [N,H,W] planes (N = B*C).

@@ -304,3 +304,18 @@ def test_batch_one_is_bit_exact_too(hw):
     assert abs(float(go["total"].detach()) - float(ro["total"].detach())) <= 1e-5 * abs(float(ro["total"].detach()))
     for j in range(3):
         assert rel_l2(gd[j].grad, rd[j].grad) < 1e-4, (hw, j, rel_l2(gd[j].grad, rd[j].grad))
+
+
+def test_pft_window_cuda_graph_matches_eager():
+    """The whole optimisation epoch (stand-in networks + fused path + backward + Adam) replayed as
+    a CUDA graph gives the same loss trajectory as eager execution."""
+    from tcsfm_b200 import pft_driver
+    b, h, w = 2, 64, 96
+    fr = frames(b, h, w, 0.01, synth.KITTI_DEPTH_RANGE, seed=9)
+    depth_net, pose_net = synth.TinyDepthNet(seed=3).to(DEV), synth.TinyPoseNet(seed=3).to(DEV)
+    opts = {"epochs": 7}
+    eager = pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts, iterations=3)
+    graph = pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts, iterations=3,
+                                       cuda_graph=True)
+    assert graph["losses"].shape == eager["losses"].shape == (7,)
+    assert torch.allclose(graph["losses"], eager["losses"], rtol=1e-4, atol=0), (graph["losses"], eager["losses"])

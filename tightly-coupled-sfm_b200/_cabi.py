@@ -2,7 +2,7 @@
 package loader and by the test-only emulator binding)."""
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ARITH_CPU = 1 << 0
 AUTO_MASK = 1 << 1
@@ -38,9 +38,9 @@ class FrameCfg(C.Structure):
 SIGNATURES = {
     "tcsfm_last_error": (C.c_char_p, []),
     "tcsfm_abi_version": (C.c_int, []),
-    "tcsfm_warp_fwd": (C.c_int, [_fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+    "tcsfm_warp_fwd": (C.c_int, [_fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i64, _i64, _fp,
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "tcsfm_warp_bwd": (C.c_int, [_fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+    "tcsfm_warp_bwd": (C.c_int, [_fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tcsfm_ssim_fwd": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tcsfm_ssim_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -46,7 +46,9 @@ def image_view(img, name="img"):
     return img, (img.stride(0) if b > 1 else c * h * w), (img.stride(1) if c > 1 else h * w)
 
 
-def warp_fwd(lib, img, depth, ref_depth, kinv, proj, flags=0, need_depths=True):
+def warp_fwd(lib, img, depth, ref_depth, kinv, proj, flags=0, need_depths=True, stack_target=None):
+    """stack_target: optional [B,3,H,W] view of the reconstruction target; when given the kernel
+    also writes the next pose-network input [target * valid | projected_img] ([B,6,H,W])."""
     b, _, h, w = img.shape
     img, sb, sc = image_view(img)
     depth, ref_depth = _f32c(depth, "depth"), _f32c(ref_depth, "ref_depth")
@@ -55,22 +57,29 @@ def warp_fwd(lib, img, depth, ref_depth, kinv, proj, flags=0, need_depths=True):
     out_valid = torch.empty((b, 1, h, w), dtype=torch.float32, device=img.device)
     out_pd = torch.empty_like(out_valid) if need_depths else None
     out_cd = torch.empty_like(out_valid) if need_depths else None
+    tgt, tsb, tsc, stack = None, 0, 0, None
+    if stack_target is not None:
+        tgt, tsb, tsc = image_view(stack_target, "stack_target")
+        stack = torch.empty((b, 6, h, w), dtype=torch.float32, device=img.device)
     with _timing.launch("warp_fwd", img.is_cuda):
         rc = lib.tcsfm_warp_fwd(_ptr(img), sb, sc, _ptr(depth), _ptr(ref_depth), _ptr(kinv), _ptr(proj),
                                 _ptr(out_img), _ptr(out_valid), _ptr(out_pd), _ptr(out_cd),
-                                b, h, w, flags, _stream(img))
+                                _ptr(tgt), tsb, tsc, _ptr(stack), b, h, w, flags, _stream(img))
     _cabi.check(lib, rc)
     _timing.count_launch()
+    if stack_target is not None:
+        return out_img, out_valid, out_pd, out_cd, stack
     return out_img, out_valid, out_pd, out_cd
 
 
 def warp_bwd(lib, img, depth, ref_depth, kinv, proj, g_img, g_pd, g_cd, flags=0,
-             need_img_grad=False, need_ref_depth_grad=True):
+             need_img_grad=False, need_ref_depth_grad=True, g_stack=None):
     b, _, h, w = img.shape
     img, sb, sc = image_view(img)
     depth, ref_depth = _f32c(depth, "depth"), _f32c(ref_depth, "ref_depth")
     kinv, proj = _f32c(kinv, "kinv"), _f32c(proj, "proj")
     g_img, g_pd, g_cd = _f32c(g_img, "g_img"), _f32c(g_pd, "g_pd"), _f32c(g_cd, "g_cd")
+    g_stack = _f32c(g_stack, "g_stack")
     dev = img.device
     g_depth = torch.empty((b, 1, h, w), dtype=torch.float32, device=dev)
     g_ref = torch.empty((b, 1, h, w), dtype=torch.float32, device=dev) if need_ref_depth_grad else None
@@ -78,7 +87,7 @@ def warp_bwd(lib, img, depth, ref_depth, kinv, proj, g_img, g_pd, g_cd, flags=0,
     g_src = torch.empty((b, 3, h, w), dtype=torch.float32, device=dev) if need_img_grad else None
     with _timing.launch("warp_bwd", img.is_cuda):
         rc = lib.tcsfm_warp_bwd(_ptr(img), sb, sc, _ptr(depth), _ptr(ref_depth), _ptr(kinv), _ptr(proj),
-                                _ptr(g_img), _ptr(g_pd), _ptr(g_cd),
+                                _ptr(g_img), _ptr(g_pd), _ptr(g_cd), _ptr(g_stack),
                                 _ptr(g_depth), _ptr(g_ref), _ptr(g_proj), _ptr(g_src),
                                 b, h, w, flags, _stream(img))
     _cabi.check(lib, rc)

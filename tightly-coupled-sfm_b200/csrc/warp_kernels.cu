@@ -17,7 +17,8 @@ warp_fwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
                 const float* __restrict__ depth, const float* __restrict__ ref_depth,
                 const float* __restrict__ kinv, const float* __restrict__ proj,
                 float* __restrict__ out_img, float* __restrict__ out_valid,
-                float* __restrict__ out_pd, float* __restrict__ out_cd, Arith A) {
+                float* __restrict__ out_pd, float* __restrict__ out_cd,
+                const float* __restrict__ tgt, int64_t tgt_sb, int64_t tgt_sc, float* __restrict__ out_stack, Arith A) {
     const int b = blockIdx.y;
     const int n = A.H * A.W;
     const int pix = blockIdx.x * kWarpThreads + threadIdx.x;
@@ -27,10 +28,16 @@ warp_fwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
     const int64_t o = (int64_t)b * n + pix;
     WarpPt p;
     warp_point<F>(c, A, u, v, __ldg(depth + o), p);
-    if (out_img) {
+    if (out_img || out_stack) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-            out_img[((int64_t)b * 3 + ch) * n + pix] = sample_plane(img + b * img_sb + ch * img_sc, p, A.H, A.W);
+        for (int ch = 0; ch < 3; ++ch) {
+            const float w = sample_plane(img + b * img_sb + ch * img_sc, p, A.H, A.W);
+            if (out_img) out_img[((int64_t)b * 3 + ch) * n + pix] = w;
+            if (out_stack) {          // next pose-net input: [target * valid | reconstruction], train_mono.py:74-76
+                out_stack[((int64_t)b * 6 + 3 + ch) * n + pix] = w;
+                out_stack[((int64_t)b * 6 + ch) * n + pix] = __fmul_rn(__ldg(tgt + b * tgt_sb + ch * tgt_sc + pix), p.valid ? 1.f : 0.f);
+            }
+        }
     }
     if (out_valid) out_valid[o] = p.valid ? 1.f : 0.f;
     if (out_pd) out_pd[o] = sample_plane(ref_depth + (int64_t)b * n, p, A.H, A.W);
@@ -53,6 +60,7 @@ warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
                 const float* __restrict__ depth, const float* __restrict__ ref_depth,
                 const float* __restrict__ kinv, const float* __restrict__ proj,
                 const float* __restrict__ g_oimg, const float* __restrict__ g_opd, const float* __restrict__ g_ocd,
+                const float* __restrict__ g_ostack,
                 float* __restrict__ g_depth, float* __restrict__ g_ref_depth, float* __restrict__ g_proj,
                 float* __restrict__ g_img, Arith A) {
     TCSFM_SHARED float red[12 * (kWarpThreads / 32)];
@@ -69,10 +77,11 @@ warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
         WarpPt p;
         warp_point<F>(c, A, u, v, __ldg(depth + o), p);
         float g_ix = 0.f, g_iy = 0.f;
-        if (g_oimg) {
+        if (g_oimg || g_ostack) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const float g = __ldg(g_oimg + ((int64_t)b * 3 + ch) * n + pix);
+                float g = g_oimg ? __ldg(g_oimg + ((int64_t)b * 3 + ch) * n + pix) : 0.f;
+                if (g_ostack) g += __ldg(g_ostack + ((int64_t)b * 6 + 3 + ch) * n + pix);
                 const Taps t = gather_taps(img + b * img_sb + ch * img_sc, p, A.H, A.W);
                 bilinear_grad(t, p, g, g_ix, g_iy);
                 if (g_img) scatter_taps(g_img + ((int64_t)b * 3 + ch) * n, p, g, A.H, A.W);
@@ -106,16 +115,19 @@ extern "C" int tcsfm_warp_fwd(const float* img, int64_t img_sb, int64_t img_sc,
                               const float* depth, const float* ref_depth,
                               const float* kinv, const float* proj,
                               float* out_img, float* out_valid, float* out_proj_depth, float* out_comp_depth,
+                              const float* tgt, int64_t tgt_sb, int64_t tgt_sc, float* out_stack,
                               int B, int H, int W, int flags, void* stream) {
     if (B <= 0 || H < 2 || W < 2) { set_error("tcsfm_warp_fwd: bad shape B=%d H=%d W=%d", B, H, W); return 1; }
     if (!img || !depth || !kinv || !proj || (out_proj_depth && !ref_depth)) {
         set_error("tcsfm_warp_fwd: null input pointer"); return 1;
     }
     if (B > 65535) { set_error("tcsfm_warp_fwd: B=%d exceeds 65535", B); return 1; }
+    if (out_stack && !tgt) { set_error("tcsfm_warp_fwd: out_stack needs the target image"); return 1; }
     const Arith A = make_arith(H, W, flags);
     dim3 grid((H * W + kWarpThreads - 1) / kWarpThreads, B), block(kWarpThreads);
     TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(warp_fwd_kernel<F>, grid, block, 0, stream, img, img_sb, img_sc, depth,
-                                               ref_depth, kinv, proj, out_img, out_valid, out_proj_depth, out_comp_depth, A));
+                                               ref_depth, kinv, proj, out_img, out_valid, out_proj_depth, out_comp_depth,
+                                               tgt, tgt_sb, tgt_sc, out_stack, A));
     return check_launch("tcsfm_warp_fwd");
 }
 
@@ -123,6 +135,7 @@ extern "C" int tcsfm_warp_bwd(const float* img, int64_t img_sb, int64_t img_sc,
                               const float* depth, const float* ref_depth,
                               const float* kinv, const float* proj,
                               const float* g_out_img, const float* g_out_proj_depth, const float* g_out_comp_depth,
+                              const float* g_out_stack,
                               float* g_depth, float* g_ref_depth, float* g_proj, float* g_img,
                               int B, int H, int W, int flags, void* stream) {
     if (B <= 0 || H < 2 || W < 2) { set_error("tcsfm_warp_bwd: bad shape B=%d H=%d W=%d", B, H, W); return 1; }
@@ -135,7 +148,7 @@ extern "C" int tcsfm_warp_bwd(const float* img, int64_t img_sb, int64_t img_sc,
     if (g_img) cudaMemsetAsync(g_img, 0, 3 * plane, (cudaStream_t)stream);
     dim3 grid((H * W + kWarpThreads - 1) / kWarpThreads, B), block(kWarpThreads);
     TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(warp_bwd_kernel<F>, grid, block, 0, stream, img, img_sb, img_sc, depth,
-                                               ref_depth, kinv, proj, g_out_img, g_out_proj_depth, g_out_comp_depth,
+                                               ref_depth, kinv, proj, g_out_img, g_out_proj_depth, g_out_comp_depth, g_out_stack,
                                                g_depth, g_ref_depth, g_proj, g_img, A));
     return check_launch("tcsfm_warp_bwd");
 }

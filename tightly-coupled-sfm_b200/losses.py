@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi, ops
-from .stn import pose_vec2mat
+from .stn import inverse_intrinsics, pose_vec2mat
 
 
 class SSIM_Loss(nn.Module):
@@ -49,23 +49,6 @@ def get_smooth_loss(disp, img):
     grad_disp_x = grad_disp_x * torch.exp(-grad_img_x)
     grad_disp_y = grad_disp_y * torch.exp(-grad_img_y)
     return grad_disp_x.mean() + grad_disp_y.mean()
-
-
-_KINV_CACHE = {}
-
-
-def inverse_intrinsics(intrinsics):
-    """`intrinsics.inverse()` (models/stn.py:257), memoised per tensor version: K is a loader
-    output that stays constant across the warps/losses of a step, and the batched LU costs
-    half a dozen launches."""
-    key = (intrinsics.data_ptr(), intrinsics._version, intrinsics.device, tuple(intrinsics.shape))
-    hit = _KINV_CACHE.get(key)
-    if hit is None:
-        if len(_KINV_CACHE) > 64:
-            _KINV_CACHE.clear()
-        hit = (intrinsics.detach().inverse(), intrinsics)      # keeps K alive so the pointer stays unique
-        _KINV_CACHE[key] = hit
-    return hit[0]
 
 
 def _pair_flags(config):

@@ -40,30 +40,32 @@ def _require_cuda(*tensors):
 
 
 class InverseWarp2Fn(torch.autograd.Function):
-    """(img, depth, ref_depth, kinv, proj) -> (projected_img, valid_mask,
-    projected_depth, computed_depth); kernels: csrc/warp_kernels.cu."""
+    """(img, depth, ref_depth, kinv, proj[, stack_target]) -> (projected_img, valid_mask,
+    projected_depth, computed_depth[, stack]); kernels: csrc/warp_kernels.cu.  With a
+    `stack_target` (the [B,3,H,W] reconstruction target) the forward also emits the next
+    pose-network input [target * valid_mask | projected_img] of train_mono.py:74-76."""
 
     @staticmethod
-    def forward(ctx, img, depth, ref_depth, kinv, proj):
-        _require_cuda(img, depth, ref_depth, kinv, proj)
+    def forward(ctx, img, depth, ref_depth, kinv, proj, stack_target=None):
+        _require_cuda(img, depth, ref_depth, kinv, proj, stack_target)
         ctx.set_materialize_grads(False)
         ctx.flags = arith_flags(img.shape[0], img.shape[2], img.shape[3])
         with _guard(img):
-            out_img, valid, pd, cd = _raw.warp_fwd(lib(), img, depth, ref_depth, kinv, proj, ctx.flags)
+            outs = _raw.warp_fwd(lib(), img, depth, ref_depth, kinv, proj, ctx.flags, stack_target=stack_target)
         ctx.save_for_backward(img, depth, ref_depth, kinv, proj)
-        ctx.mark_non_differentiable(valid)
-        return out_img, valid, pd, cd
+        ctx.mark_non_differentiable(outs[1])
+        return outs
 
     @staticmethod
-    def backward(ctx, g_img, g_valid, g_pd, g_cd):
+    def backward(ctx, g_img, g_valid, g_pd, g_cd, g_stack=None):
         img, depth, ref_depth, kinv, proj = ctx.saved_tensors
         need_img = ctx.needs_input_grad[0]
         need_ref = ctx.needs_input_grad[2]
         with _guard(img):
             g_depth, g_ref, g_proj, g_src = _raw.warp_bwd(
                 lib(), img, depth, ref_depth, kinv, proj, g_img, g_pd, g_cd, ctx.flags,
-                need_img_grad=need_img, need_ref_depth_grad=need_ref)
-        return g_src, g_depth, g_ref, None, g_proj
+                need_img_grad=need_img, need_ref_depth_grad=need_ref, g_stack=g_stack)
+        return g_src, g_depth, g_ref, None, g_proj, None
 
 
 class SsimFn(torch.autograd.Function):

@@ -32,30 +32,63 @@ class Backend:
 
 
 def optimize_window(depth_net, pose_net, target_img, source_imgs, intrinsics, options=None, iterations=4,
-                    depth_range=(0.06, 2.67), backend=Backend):
+                    depth_range=(0.06, 2.67), backend=Backend, cuda_graph=False):
     """One window minibatch (optimizer.py:136-297).  Returns dict(losses=[per-epoch loss tensors],
-    disparity=final target disparity, poses=..., poses_inv=...)."""
+    disparity=final target disparity, poses=..., poses_inv=...).
+
+    cuda_graph=True captures one optimisation epoch (networks, hot path, backward, Adam) into a
+    CUDA graph after three eager epochs and replays it for the rest: the fused path has no host
+    synchronisation or data-dependent control flow, so the whole epoch is capturable."""
     opts = dict(DEFAULT_OPTIONS, **(options or {}))
     bsz = target_img.shape[0]
     imgs = torch.cat([target_img] + list(source_imgs), 0)
     with torch.no_grad():                                    # un-optimised prediction, optimizer.py:143-160
         init_disp = depth_net(imgs)[0][0:bsz].clone()
     net = copy.deepcopy(depth_net)                            # optimizer.py:177-182
-    optim = torch.optim.Adam(net.encoder.parameters(), lr=opts["lr"])
-    loss_log, out = [], {}
-    for epoch in range(opts["epochs"]):                       # optimizer.py:217-268
-        optim.zero_grad(set_to_none=True)
+    optim = torch.optim.Adam(net.encoder.parameters(), lr=opts["lr"], capturable=bool(cuda_graph))
+    state = {}
+
+    def forward():                                            # optimizer.py:217-263
         disp = net(imgs)[0]
         disps = [disp[i * bsz:(i + 1) * bsz] for i in range(1 + len(source_imgs))]
         depths = [backend.disp_to_depth(d, depth_range[0], depth_range[1])[1] for d in disps]
         poses, poses_inv, outputs = backend.solve_pose_iteratively(
             iterations, depths, pose_net, target_img, list(source_imgs), intrinsics, return_errors=True)
         loss = backend.compute_optimization_loss(opts, target_img, disps[0], init_disp, outputs["fwd"], outputs["inv"])
-        loss_log.append(loss.detach().reshape(()))
-        if epoch != opts["epochs"] - 1:
-            loss.sum().backward()
-            optim.step()
-        out = {"disparity": disps[0].detach(), "poses": [p.detach() for p in poses],
-               "poses_inv": [p.detach() for p in poses_inv]}
+        state.update(disparity=disps[0].detach(), poses=[p.detach() for p in poses],
+                     poses_inv=[p.detach() for p in poses_inv])
+        return loss
+
+    def train_step():                                         # optimizer.py:266-268
+        optim.zero_grad(set_to_none=True)
+        loss = forward()
+        loss.sum().backward()
+        optim.step()
+        return loss
+
+    loss_log = []
+    n_train = opts["epochs"] - 1                              # the last epoch only evaluates
+    if not cuda_graph:
+        for _ in range(n_train):
+            loss_log.append(train_step().detach().reshape(()))
+    else:
+        warm = min(3, n_train)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warm):
+                loss_log.append(train_step().detach().reshape(()).clone())
+        torch.cuda.current_stream().wait_stream(side)
+        if n_train > warm:
+            graph = torch.cuda.CUDAGraph()
+            optim.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                static_loss = train_step()
+            for _ in range(n_train - warm):
+                graph.replay()
+                loss_log.append(static_loss.detach().reshape(()).clone())
+    with torch.no_grad():
+        loss_log.append(forward().detach().reshape(()))
+    out = dict(state)
     out["losses"] = torch.stack(loss_log)
     return out

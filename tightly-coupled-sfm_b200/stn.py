@@ -76,9 +76,33 @@ def pose_vec2mat(vec, rotation_mode='euler'):
     return torch.cat([rot_mat, translation], dim=2)
 
 
-def projection_matrices(pose, intrinsics):
-    """(K^-1, K @ [R|t]) exactly as models/stn.py:257-262 forms them."""
-    return intrinsics.inverse(), intrinsics @ pose_vec2mat(pose[:, 0:6])
+_KINV_CACHE = {}
+
+
+def inverse_intrinsics(intrinsics):
+    """`intrinsics.inverse()` (models/stn.py:257), memoised per tensor version: K is a loader
+    output that stays constant across the warps/losses of a step, and the batched LU costs
+    half a dozen launches (and cannot be captured into a CUDA graph)."""
+    key = (intrinsics.data_ptr(), intrinsics._version, intrinsics.device, tuple(intrinsics.shape))
+    hit = _KINV_CACHE.get(key)
+    if hit is None:
+        if len(_KINV_CACHE) > 64:
+            _KINV_CACHE.clear()
+        hit = (intrinsics.detach().inverse(), intrinsics)      # keeps K alive so the pointer stays unique
+        _KINV_CACHE[key] = hit
+    return hit[0]
+
+
+def projection_matrices(pose, intrinsics, kinv=None):
+    """(K^-1, K @ [R|t]) as models/stn.py:257-262 forms them.  On the GPU with a batch of at
+    least two poses the 25-kernel euler/bmm chain is one fused launch that reproduces it bit for
+    bit (csrc/frame_kernels.cu); batch 1 takes the eager operators because cuBLAS switches to a
+    differently rounded kernel there."""
+    if kinv is None:
+        kinv = inverse_intrinsics(intrinsics)
+    if pose.is_cuda and pose.shape[0] >= 2 and not intrinsics.requires_grad:
+        return kinv, ops.PoseProjFn.apply(pose[:, 0:6], intrinsics, 1.0)
+    return kinv, intrinsics @ pose_vec2mat(pose[:, 0:6])
 
 
 def inverse_warp2(img, depth, ref_depth, pose, intrinsics, padding_mode='zeros'):
@@ -103,6 +127,14 @@ def inverse_warp2(img, depth, ref_depth, pose, intrinsics, padding_mode='zeros')
                                   "(no reference call site differentiates them)")
     kinv, proj = projection_matrices(pose, intrinsics)
     return ops.InverseWarp2Fn.apply(img, depth, ref_depth, kinv, proj)
+
+
+def inverse_warp2_stacked(img, depth, ref_depth, pose, intrinsics, kinv, stack_target):
+    """inverse_warp2 plus the next pose-network input of solve_pose_iteratively
+    (train_mono.py:74-76): returns (projected_img, valid_mask, projected_depth, computed_depth,
+    stack) with stack = [stack_target * valid_mask | projected_img] as one [B,6,H,W] tensor."""
+    kinv, proj = projection_matrices(pose, intrinsics, kinv)
+    return ops.InverseWarp2Fn.apply(img, depth, ref_depth, kinv, proj, stack_target)
 
 
 # ---- legacy helpers kept importable (no live callers in the reference) ----------

@@ -8,7 +8,7 @@ import torch
 
 from . import ops
 from .losses import SSIM_Loss
-from .stn import inverse_warp2
+from .stn import inverse_intrinsics, inverse_warp2_stacked
 
 
 def compute_pose_consistency_loss(poses, poses_inv):
@@ -62,24 +62,28 @@ def solve_pose_iteratively(num_iter, depths, pose_model, target_img, source_img_
     depth, source_depths = depths[0], torch.cat(depths[1:], 0)
     target_depths = depth.repeat(n_src, 1, 1, 1)
     source_imgs = torch.cat(source_img_list, 0)
+    intrinsics_in = intrinsics
     intrinsics = intrinsics.repeat(2 * n_src, 1, 1)
     target_imgs = target_img.repeat(n_src, 1, 1, 1)
     imgs = torch.cat([torch.cat([target_imgs, source_imgs], 1), torch.cat([source_imgs, target_imgs], 1)], 0)
     tgt_depth_full = torch.cat([target_depths, source_depths], 0)
     src_depth_full = torch.cat([source_depths, target_depths], 0)
 
+    kinv = inverse_intrinsics(intrinsics_in).repeat(2 * n_src, 1, 1)
+    tgt_view, src_view = imgs[:, 0:3], imgs[:, 3:6]
+
+    def warp(poses):
+        # one launch: the reconstruction, its masks/depths and the next pose-net input
+        # [target * valid | reconstruction] (train_mono.py:69-76,80)
+        return inverse_warp2_stacked(src_view, tgt_depth_full, src_depth_full, -poses, intrinsics, kinv, tgt_view)
+
     full_poses = pose_model(imgs)
     stacked = [full_poses.clone()]
-    img_rec, valid_mask, proj_d, comp_d = inverse_warp2(imgs[:, 3:6], tgt_depth_full, src_depth_full,
-                                                        -full_poses, intrinsics, 'zeros')
+    img_rec, valid_mask, proj_d, comp_d, new_imgs = warp(full_poses)
     for _ in range(num_iter - 1):
-        new_imgs = imgs.clone()
-        new_imgs[:, 0:3] = new_imgs[:, 0:3] * valid_mask
-        new_imgs[:, 3:6] = img_rec
         full_poses = full_poses + pose_model(new_imgs)
         stacked.append(full_poses.clone())
-        img_rec, valid_mask, proj_d, comp_d = inverse_warp2(imgs[:, 3:6], tgt_depth_full, src_depth_full,
-                                                            -full_poses, intrinsics, 'zeros')
+        img_rec, valid_mask, proj_d, comp_d, new_imgs = warp(full_poses)
     stacked = torch.stack(stacked, 1)                       # [2*S*B, num_iter, 6]
 
     outputs = {'fwd': {}, 'inv': {}}
@@ -89,9 +93,6 @@ def solve_pose_iteratively(num_iter, depths, pose_model, target_img, source_img_
             outputs[name] = {'diff_img': diff[sl], 'img_rec': img_rec[sl], 'valid_mask': valid_mask[sl],
                              'weight_mask': weight[sl], 'poses': stacked[sl],
                              'auto_mask_error': auto_err[sl], 'auto_mask': auto_mask[sl]}
-        new_imgs = imgs.clone()
-        new_imgs[:, 0:3] = new_imgs[:, 0:3] * valid_mask
-        new_imgs[:, 3:6] = img_rec
         outputs['comb'] = {'imgs': new_imgs, 'valid_mask': valid_mask}
 
     last = stacked[:, -1]
