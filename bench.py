@@ -51,6 +51,11 @@ WORKLOADS = {
     # name: (B, H, W, n_src, depth_range key, intrinsics)
     "kitti": dict(b=8, h=192, w=640, n_src=2, desc="kitti_triplets_b8_192x640_fwd+inv_ssim_l1_automask_depthconsist"),
     "scannet": dict(b=16, h=256, w=320, n_src=1, desc="scannet_pairs_b16_256x320_fwd+inv_ssim_l1_automask_depthconsist"),
+    "scannet448": dict(b=16, h=256, w=448, n_src=1, desc="scannet_pairs_b16_256x448_fwd+inv_ssim_l1_automask_depthconsist"),
+    # config 5: the training-step loss path at 4 scales (every scale nearest-upsampled to full
+    # resolution, losses.py:86-87) at 376x1242
+    "kitti376x4": dict(b=2, h=376, w=1242, n_src=2, scales=4,
+                       desc="kitti_triplets_b2_376x1242_4scales_fwd+inv_ssim_l1_automask_depthconsist"),
 }
 LOSS_CFG = {"l1_weight": 0.15, "l_ssim_weight": 0.85, "l_smooth_weight": 0.05, "num_scales": 1,
             "l_depth_consist_weight": 0.14, "min_depth": 0.06, "max_depth": 2.67, "l_smooth": False,
@@ -62,10 +67,15 @@ N_INPUT_SETS = 8      # rotating input sets: 8 x ~47 MB > 126 MB of L2, so no st
 
 def make_inputs(wl, seed, device, pin=False):
     from tcsfm_b200 import synth
-    rng = synth.KITTI_DEPTH_RANGE if wl["h"] == 192 else synth.SCANNET_DEPTH_RANGE
-    base = synth.KITTI_K if wl["h"] == 192 else synth.SCANNET_K
-    fr = synth.make_frames(wl["b"], wl["h"], wl["w"], n_src=wl["n_src"], seed=seed, depth_range=rng,
-                           intrinsics=torch.tensor(base, dtype=torch.float32))
+    kitti = wl["h"] in (192, 376)
+    rng = synth.KITTI_DEPTH_RANGE if kitti else synth.SCANNET_DEPTH_RANGE
+    if wl["h"] == 376:
+        base = torch.tensor(synth.KITTI_FULL_K, dtype=torch.float32)
+    elif kitti:
+        base = torch.tensor(synth.KITTI_K, dtype=torch.float32)
+    else:
+        base = synth.scaled_intrinsics(wl["h"], wl["w"], synth.SCANNET_K, (256, 320))
+    fr = synth.make_frames(wl["b"], wl["h"], wl["w"], n_src=wl["n_src"], seed=seed, depth_range=rng, intrinsics=base)
     flat = {"target": fr["target"], "K": fr["K"]}
     for j in range(wl["n_src"]):
         flat["source%d" % j] = fr["sources"][j]
@@ -73,19 +83,23 @@ def make_inputs(wl, seed, device, pin=False):
         flat["pose_inv%d" % j] = fr["poses_inv"][j]
     for j in range(1 + wl["n_src"]):
         flat["disp%d" % j] = fr["disps"][j]
+        for sc in range(1, wl.get("scales", 1)):          # lower-resolution disparities of the other scales
+            flat["disp%d_s%d" % (j, sc)] = torch.nn.functional.avg_pool2d(fr["disps"][j], 2 ** sc, ceil_mode=True)
     if pin:
         return {k: v.pin_memory() for k, v in flat.items()}
     return {k: v.to(device) for k, v in flat.items()}
 
 
 def run_step(loss_mod, inp, n_src, need_value=False):
+    n_scales = loss_mod.num_scales
     disps = [inp["disp%d" % j].requires_grad_(True) for j in range(1 + n_src)]
+    extra = [[inp["disp%d_s%d" % (j, sc)].requires_grad_(True) for sc in range(1, n_scales)] for j in range(1 + n_src)]
     poses = [inp["pose%d" % j].requires_grad_(True) for j in range(n_src)]
     poses_inv = [inp["pose_inv%d" % j].requires_grad_(True) for j in range(n_src)]
-    for t in disps + poses + poses_inv:
+    for t in disps + poses + poses_inv + [e for ex in extra for e in ex]:
         t.grad = None
     out = loss_mod([inp["source%d" % j] for j in range(n_src)], inp["target"], [poses, poses_inv],
-                   [[d] for d in disps], inp["K"])
+                   [[d] + ex for d, ex in zip(disps, extra)], inp["K"])
     total = out["total"].sum()
     total.backward()
     return total
@@ -128,12 +142,20 @@ def cpu_port_throughput(wl, steps, warmup, threads):
     inp = make_inputs(wl, 0, "cpu")
     n_src = wl["n_src"]
 
+    n_scales = wl.get("scales", 1)
+    kitti = wl["h"] in (192, 376)
+    from tcsfm_b200 import synth
+    rng = synth.KITTI_DEPTH_RANGE if kitti else synth.SCANNET_DEPTH_RANGE
+    cfg = dict(LOSS_CFG, num_scales=n_scales, min_depth=rng[0], max_depth=rng[1])
+
     def step():
-        disps = [inp["disp%d" % j].clone().requires_grad_(True) for j in range(1 + n_src)]
+        disps = [[inp["disp%d" % j].clone().requires_grad_(True)] +
+                 [inp["disp%d_s%d" % (j, sc)].clone().requires_grad_(True) for sc in range(1, n_scales)]
+                 for j in range(1 + n_src)]
         poses = [inp["pose%d" % j].clone().requires_grad_(True) for j in range(n_src)]
         poses_inv = [inp["pose_inv%d" % j].clone().requires_grad_(True) for j in range(n_src)]
-        out = O.compute_loss(LOSS_CFG, [inp["source%d" % j] for j in range(n_src)], inp["target"],
-                             [poses, poses_inv], [[d] for d in disps], inp["K"])
+        out = O.compute_loss(cfg, [inp["source%d" % j] for j in range(n_src)], inp["target"],
+                             [poses, poses_inv], disps, inp["K"])
         out["total"].sum().backward()
         return float(out["total"].sum().detach())
 
@@ -290,7 +312,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    config = {"workload": wl["desc"], "batch_per_gpu": wl["b"], "pairs_per_step_per_gpu": 2 * wl["n_src"] * wl["b"],
+    config = {"workload": wl["desc"], "batch_per_gpu": wl["b"],
+              "pairs_per_step_per_gpu": 2 * wl["n_src"] * wl["b"] * wl.get("scales", 1),
               "height": wl["h"], "width": wl["w"], "flags": "full (depth-consistency mask + term, auto-mask, SSIM+L1)",
               "parallelism": "shard%d" % max(world, args.gpus),
               "l2": "inputs rotate over %d sets (> L2 capacity)" % N_INPUT_SETS}
@@ -321,8 +344,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from tcsfm_b200 import _timing, losses
-    loss_mod = losses.Compute_Loss(LOSS_CFG)
+    from tcsfm_b200 import _timing, losses, synth
+    kitti = wl["h"] in (192, 376)
+    rng = synth.KITTI_DEPTH_RANGE if kitti else synth.SCANNET_DEPTH_RANGE
+    loss_mod = losses.Compute_Loss(dict(LOSS_CFG, num_scales=wl.get("scales", 1), min_depth=rng[0], max_depth=rng[1]))
     n_src = wl["n_src"]
     sets = [make_inputs(wl, 100 * rank + s, dev) for s in range(N_INPUT_SETS)]
     host_sets = [make_inputs(wl, 100 * rank + s, dev, pin=True) for s in range(2)]
@@ -449,9 +474,10 @@ def main():
     e2e_value = frames * e2e_steps / (ms_e2e / 1e3)
     h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
     npx = wl["h"] * wl["w"]
-    pairs = 2 * n_src * wl["b"]
+    pairs = 2 * n_src * wl["b"] * wl.get("scales", 1)
     # algorithmic bytes per pixel per pair (SURVEY.md §8d / DESIGN.md): fwd 32 R + 8 W, bwd 36 R + 8 W
-    bytes_per_launch = {"pair_loss_fwd": 40 * npx * pairs, "pair_loss_bwd": 44 * npx * pairs}
+    per_launch_pairs = 2 * n_src * wl["b"]
+    bytes_per_launch = {"pair_loss_fwd": 40 * npx * per_launch_pairs, "pair_loss_bwd": 44 * npx * per_launch_pairs}
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -477,7 +503,8 @@ def main():
         cpu_baseline = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port", "ms_per_step": cms,
                         "sample": "%d steps of one B=%d minibatch of the same workload (oracle port of the "
                                   "reference's PyTorch CPU path, torch threads=%d)" % (csteps, wl["b"], cores)}
-    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+    metric = METRIC if args.workload == "kitti" else "warp+SSIM/L1 loss fwd+bwd frames/s at %dx%d" % (wl["h"], wl["w"])
+    line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "pairs_per_s": value * 2 * n_src, "clocks": clocks,
