@@ -152,6 +152,14 @@ int tcsfm_photo_bwd(const float* tgt, int64_t tgt_sb, int64_t tgt_sc, const floa
                     const float* g_diff, const float* g_weight, float* g_rec, float* g_pd, float* g_cd,
                     int N, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
 
+/* ---- get_smooth_loss (losses.py:43-61): edge-aware smoothness of the mean-normalised disparity --
+ * disp [B,1,H,W] contiguous, img [B,3,H,W] view; workspace: 2*B+2 floats kept between forward and
+ * backward; out / g_out: device scalars; g_disp [B,1,H,W]. */
+int tcsfm_smooth_fwd(const float* disp, const float* img, int64_t img_sb, int64_t img_sc,
+                     float* workspace, float* out, int B, int H, int W, void* stream);
+int tcsfm_smooth_bwd(const float* disp, const float* img, int64_t img_sb, int64_t img_sc,
+                     float* workspace, const float* g_out, float* g_disp, int B, int H, int W, void* stream);
+
 /* ---- glue of Compute_Loss.forward (losses.py:75-140) ----------------------------
  * pose [N,6] (times `sign`; every call site passes -pose) -> K @ [Rx Ry Rz | t] as [N,12]
  * (models/stn.py:81-116,143-158,262); row i uses K[i % Bk].  Bit-identical to the eager

@@ -211,3 +211,20 @@ def test_pft_driver_matches_oracle_backend(emu_ops):
     assert (got["disparity"] - ref["disparity"]).abs().max() < 1e-6
     # the caller's network is untouched: every window starts from the same weights
     assert all(torch.equal(a, b) for a, b in zip(depth_net.state_dict().values(), synth.TinyDepthNet(seed=2).state_dict().values()))
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 40), (3, 17, 33), (1, 2, 2)])
+def test_smooth_loss_vs_oracle(emu_ops, shape):
+    from oracle import ref_torch as O
+    b, h, w = shape
+    gen = torch.Generator().manual_seed(b * 100 + h)
+    img = torch.rand(b, 3, h, w, generator=gen)
+    d_ref = torch.rand(b, 1, h, w, generator=gen).add_(0.05).requires_grad_(True)
+    d_got = d_ref.detach().clone().requires_grad_(True)
+    ref = O.smooth_loss(d_ref, img)
+    got = losses.get_smooth_loss(d_got, img)
+    assert got.shape == ref.shape == ()
+    assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+    (ref * 1.7).backward()
+    (got * 1.7).backward()
+    assert rel_l2(d_got.grad, d_ref.grad) < 1e-4

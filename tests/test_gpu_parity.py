@@ -319,3 +319,18 @@ def test_pft_window_cuda_graph_matches_eager():
                                        cuda_graph=True)
     assert graph["losses"].shape == eager["losses"].shape == (7,)
     assert torch.allclose(graph["losses"], eager["losses"], rtol=1e-4, atol=0), (graph["losses"], eager["losses"])
+
+
+@pytest.mark.parametrize("shape", [(8, 192, 640), (3, 50, 77)])
+def test_smooth_loss_vs_eager_cuda(shape):
+    """get_smooth_loss (losses.py:43-61): value within 1e-5, gradient within 1e-4 of eager PyTorch."""
+    b, h, w = shape
+    fr = frames(b, h, w, 0.01, synth.KITTI_DEPTH_RANGE, seed=4)
+    d_ref, d_got = leaf(fr["disps"][0]), leaf(fr["disps"][0])
+    six = torch.cat([fr["sources"][0], fr["target"]], 1)
+    ref = O.smooth_loss(d_ref, six[:, 3:6])
+    got = losses.get_smooth_loss(d_got, six[:, 3:6])
+    assert abs(float(got.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
+    ref.backward()
+    got.backward()
+    assert rel_l2(d_got.grad, d_ref.grad) < 1e-4

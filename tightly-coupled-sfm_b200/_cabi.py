@@ -54,6 +54,8 @@ SIGNATURES = {
                                   C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "tcsfm_photo_bwd": (C.c_int, [_fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                                   C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "tcsfm_smooth_fwd": (C.c_int, [_fp, _fp, _i64, _i64, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tcsfm_smooth_bwd": (C.c_int, [_fp, _fp, _i64, _i64, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tcsfm_pose_proj_fwd": (C.c_int, [_fp, C.c_float, _fp, C.c_int, _fp, C.c_int, C.c_void_p]),
     "tcsfm_pose_proj_bwd": (C.c_int, [_fp, C.c_float, _fp, C.c_int, _fp, _fp, C.c_int, C.c_void_p]),
     "tcsfm_disp_to_depth_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, _i64,

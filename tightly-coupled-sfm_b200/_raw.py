@@ -353,3 +353,28 @@ def disp_to_depth_bwd(lib, g_depths, depths, disp_range):
     _cabi.check(lib, rc)
     _timing.count_launch()
     return g_disps
+
+
+def smooth_fwd(lib, disp, img):
+    disp = _f32c(disp, "disp")
+    img, sb, sc = image_view(img, "img")
+    b, _, h, w = disp.shape
+    ws = torch.empty((2 * b + 2,), dtype=torch.float32, device=disp.device)
+    out = torch.empty((), dtype=torch.float32, device=disp.device)
+    with _timing.launch("smooth_fwd", disp.is_cuda):
+        rc = lib.tcsfm_smooth_fwd(_ptr(disp), _ptr(img), sb, sc, _ptr(ws), _ptr(out), b, h, w, _stream(disp))
+    _cabi.check(lib, rc)
+    _timing.count_launch(3)
+    return out, ws
+
+
+def smooth_bwd(lib, disp, img, ws, g_out):
+    disp, g_out = _f32c(disp, "disp"), _f32c(g_out, "g_out")
+    img, sb, sc = image_view(img, "img")
+    b, _, h, w = disp.shape
+    g_disp = torch.empty_like(disp)
+    with _timing.launch("smooth_bwd", disp.is_cuda):
+        rc = lib.tcsfm_smooth_bwd(_ptr(disp), _ptr(img), sb, sc, _ptr(ws), _ptr(g_out), _ptr(g_disp), b, h, w, _stream(disp))
+    _cabi.check(lib, rc)
+    _timing.count_launch(2)
+    return g_disp

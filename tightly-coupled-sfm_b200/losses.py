@@ -38,17 +38,15 @@ def disp_to_depth(disp, min_depth, max_depth):
 
 
 def get_smooth_loss(disp, img):
-    """Edge-aware smoothness of the mean-normalised disparity (reference
-    losses.py:43-61).  Not yet fused: stock PyTorch operators."""
-    mean_disp = disp.mean(2, True).mean(3, True)
-    disp = disp / (mean_disp + 1e-7)
-    grad_disp_x = torch.abs(disp[:, :, :, :-1] - disp[:, :, :, 1:])
-    grad_disp_y = torch.abs(disp[:, :, :-1, :] - disp[:, :, 1:, :])
-    grad_img_x = torch.mean(torch.abs(img[:, :, :, :-1] - img[:, :, :, 1:]), 1, keepdim=True)
-    grad_img_y = torch.mean(torch.abs(img[:, :, :-1, :] - img[:, :, 1:, :]), 1, keepdim=True)
-    grad_disp_x = grad_disp_x * torch.exp(-grad_img_x)
-    grad_disp_y = grad_disp_y * torch.exp(-grad_img_y)
-    return grad_disp_x.mean() + grad_disp_y.mean()
+    """Edge-aware smoothness of the mean-normalised disparity (reference losses.py:43-61), fused
+    into four small kernels forward + backward (csrc/smooth_kernels.cu).  Differentiable w.r.t.
+    `disp` [B,1,H,W]; the image is data."""
+    if img.requires_grad:
+        raise NotImplementedError("gradients w.r.t. the image are not implemented "
+                                  "(no reference call site differentiates them)")
+    if disp.dim() != 4 or disp.size(1) != 1 or img.dim() != 4 or img.size(1) != 3:
+        raise ValueError("get_smooth_loss expects disp [B,1,H,W] and img [B,3,H,W]")
+    return ops.SmoothLossFn.apply(disp, img)
 
 
 def _pair_flags(config):

@@ -261,3 +261,22 @@ class PhotoErrorFn(torch.autograd.Function):
             g_rec, g_pd, g_cd = _raw.photo_bwd(lib(), tgt, rec, proj_depth, comp_depth, coef, g_diff, g_weight,
                                                ctx.weights[0], ctx.weights[1], ARITH_FLAGS)
         return None, None, g_rec, g_pd, g_cd, None, None
+
+
+class SmoothLossFn(torch.autograd.Function):
+    """get_smooth_loss(disp, img) (losses.py:43-61) -> scalar; kernels: csrc/smooth_kernels.cu."""
+
+    @staticmethod
+    def forward(ctx, disp, img):
+        _require_cuda(disp, img)
+        with _guard(disp):
+            out, ws = _raw.smooth_fwd(lib(), disp, img)
+        ctx.save_for_backward(disp, img, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        disp, img, ws = ctx.saved_tensors
+        with _guard(disp):
+            g_disp = _raw.smooth_bwd(lib(), disp, img, ws, g_out)
+        return g_disp, None
