@@ -323,7 +323,11 @@ def test_pft_window_cuda_graph_matches_eager():
 
 @pytest.mark.parametrize("shape", [(8, 192, 640), (3, 50, 77)])
 def test_smooth_loss_vs_eager_cuda(shape):
-    """get_smooth_loss (losses.py:43-61): value within 1e-5, gradient within 1e-4 of eager PyTorch."""
+    """get_smooth_loss (losses.py:43-61): value within 1e-5 of eager PyTorch; gradient within 1e-4
+    away from the discontinuities.  The loss is an L1 norm of neighbour differences of the
+    mean-normalised disparity: its gradient is sign(n_p - n_q), so a pair of neighbours that agree
+    to the last few ulps flips by O(1) on any re-rounding of the mean (the reference's own
+    fp32-vs-fp64 gradient differs the same way).  Such pairs are excluded from the comparison."""
     b, h, w = shape
     fr = frames(b, h, w, 0.01, synth.KITTI_DEPTH_RANGE, seed=4)
     d_ref, d_got = leaf(fr["disps"][0]), leaf(fr["disps"][0])
@@ -333,4 +337,17 @@ def test_smooth_loss_vs_eager_cuda(shape):
     assert abs(float(got.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
     ref.backward()
     got.backward()
-    assert rel_l2(d_got.grad, d_ref.grad) < 1e-4
+    d = fr["disps"][0].double()
+    n = d / (d.mean(dim=(2, 3), keepdim=True) + 1e-7)
+    tie = torch.zeros_like(n, dtype=torch.bool)
+    near_x = (n[..., :, :-1] - n[..., :, 1:]).abs() < 1e-5
+    near_y = (n[..., :-1, :] - n[..., 1:, :]).abs() < 1e-5
+    tie[..., :, :-1] |= near_x
+    tie[..., :, 1:] |= near_x
+    tie[..., :-1, :] |= near_y
+    tie[..., 1:, :] |= near_y
+    assert tie.float().mean() < 0.01
+    keep = ~tie
+    assert rel_l2(d_got.grad[keep], d_ref.grad[keep]) < 1e-4
+    # and the discontinuities do not dominate: the full gradient still agrees to a few 1e-3
+    assert rel_l2(d_got.grad, d_ref.grad) < 2e-2
