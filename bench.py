@@ -181,7 +181,7 @@ def main_pft(args):
     rng = synth.KITTI_DEPTH_RANGE if wl["h"] == 192 else synth.SCANNET_DEPTH_RANGE
     base = synth.KITTI_K if wl["h"] == 192 else synth.SCANNET_K
     steps = min(args.steps, 4)
-    warm = min(args.warmup, 1)
+    warm = max(1, min(args.warmup, 1))
 
     def frames_for(seed, device):
         return synth.make_frames(wl["b"], wl["h"], wl["w"], n_src=wl["n_src"], seed=seed, depth_range=rng,
@@ -228,9 +228,13 @@ def main_pft(args):
     host = [{k: ([t.cpu().pin_memory() for t in v] if isinstance(v, list) else v.cpu().pin_memory()) for k, v in d.items()}
             for d in data[:2]]
 
+    runner = None if args.no_graph else pft_driver.WindowRunner(depth_net, pose_net, opts, wl["iterations"], rng)
+
     def run(fr):
+        if runner is not None:        # epoch graphs captured on the first (warm-up) window, replayed afterwards
+            return runner(fr["target"], fr["sources"], fr["K"])
         return pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts,
-                                          wl["iterations"], rng, cuda_graph=args.pft_graph)
+                                          wl["iterations"], rng)
 
     def barrier():
         if dist is not None:
@@ -282,7 +286,7 @@ def main_pft(args):
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": wl["desc"], "window_minibatches_per_gpu": steps, "parallelism": "shard%d" % world,
                                  "networks": "stand-in TinyDepthNet/TinyPoseNet (the reference nets are out of scope)",
-                                 "launch": "3 eager epochs, then CUDA-graph replay of the epoch" if args.pft_graph else "eager"},
+                                 "launch": "eager" if args.no_graph else "epoch CUDA graphs captured on the warm-up window, replayed for every timed window"},
                       "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                               "d2h_bytes_per_step": 4},
                       "gpu_launches": launches,
@@ -301,9 +305,6 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=None, help="steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of replaying CUDA graphs")
-    ap.add_argument("--pft-graph", action="store_true",
-                    help="pft workloads: capture each window's epoch into a CUDA graph (capture costs more than "
-                         "20 epochs amortise, so eager is the default)")
     args = ap.parse_args()
     if args.workload in PFT_WORKLOADS:
         return main_pft(args)

@@ -351,3 +351,18 @@ def test_smooth_loss_vs_eager_cuda(shape):
     assert rel_l2(d_got.grad[keep], d_ref.grad[keep]) < 1e-4
     # and the discontinuities do not dominate: the full gradient still agrees to a few 1e-3
     assert rel_l2(d_got.grad, d_ref.grad) < 2e-2
+
+
+def test_pft_window_runner_reuses_graphs():
+    """WindowRunner (graphs captured once, replayed for every later window) == optimize_window per window."""
+    from tcsfm_b200 import pft_driver
+    b, h, w = 2, 64, 96
+    depth_net, pose_net = synth.TinyDepthNet(seed=5).to(DEV), synth.TinyPoseNet(seed=5).to(DEV)
+    opts = {"epochs": 6}
+    runner = pft_driver.WindowRunner(depth_net, pose_net, opts, iterations=3)
+    for seed in (20, 21, 22):
+        fr = frames(b, h, w, 0.01, synth.KITTI_DEPTH_RANGE, seed=seed)
+        got = runner(fr["target"], fr["sources"], fr["K"])
+        ref = pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts, iterations=3)
+        assert torch.allclose(got["losses"], ref["losses"], rtol=1e-4, atol=0), (seed, got["losses"], ref["losses"])
+        assert (got["disparity"] - ref["disparity"]).abs().max() < 1e-4
