@@ -298,8 +298,8 @@ def main_pft(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS) + sorted(PFT_WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=None, help="steps of the CPU baseline sample")
@@ -462,7 +462,7 @@ def main():
 
     for i in range(min(args.warmup, 5)):
         step_e2e(i)
-    e2e_steps = max(5, min(args.steps, 50))
+    e2e_steps = max(5, min(args.steps, 500))
     ms_e2e = timed(step_e2e, e2e_steps)
 
     if rank != 0:
