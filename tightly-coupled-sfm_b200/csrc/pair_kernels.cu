@@ -337,10 +337,14 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         const int qx = x0 + cx, qy = y0 + cy;
         const bool inside = qx >= 0 && qx < W && qy >= 0 && qy < H;
         const int pix = inside ? qy * W + qx : 0;
+        // coefficients only matter where the upstream gradient is non-zero (masked-out pixels of
+        // the inverse groups, the losing source of the per-pixel min): skip their 36 B/px
+        const float Gd = inside ? upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, __ldg(mask + pix)) : 0.f;
+        const bool live = Gd != 0.f;
 #pragma unroll
         for (int j = 0; j < 9; ++j)
-            __pipeline_memcpy_async(cs + j * T1::kCells + cell, coef + (int64_t)j * n + pix, 4, inside ? 0 : 4);
-        Gs[cell] = inside ? upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, __ldg(mask + pix)) : 0.f;
+            __pipeline_memcpy_async(cs + j * T1::kCells + cell, coef + (int64_t)j * n + pix, 4, live ? 0 : 4);
+        Gs[cell] = Gd;
     }
     __pipeline_commit();
     __pipeline_wait_prior(0);
@@ -390,8 +394,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             const TapIdx ti = make_taps(p, H, W);
             const float m = __ldg(mask + pix);
             const float Gd = Gs[T1::cell(tx, ty0 + k)];
-            float pd = 0.f, dd = 0.f;
-            Taps td;
+            float pd = 0.f, dd = 0.f;            Taps td;
             if (need_depth) {
                 td = load_taps(c.rdep, ti, W);
                 pd = blend(td, ti);
