@@ -40,10 +40,11 @@ extern "C" {
  * (the reference's production path), flavour 1 the CPU ones (used to compare
  * bit-for-bit against CPU-generated golden vectors). */
 #define TCSFM_ARITH_CPU        (1 << 0)
-/* eager PyTorch's k=3 bmm (models/stn.py:47,210) runs a different cuBLAS kernel for batch 1 while
- * m*n*k = 9*H*W <= 2^21: (a0*b0 + a1*b1) + a2*b2 with every product and sum rounded, instead of
- * the k-ascending FMA chain (profiles/r01_probe_bmm*.json).  Set by the Python layer when the
- * reference would have issued such a call. */
+/* eager PyTorch's projection bmm `rot @ cam` (models/stn.py:210) runs a different cuBLAS kernel for
+ * batch 1 while m*n*k = 9*H*W <= 2^21: (a0*b0 + a1*b1) + a2*b2 with every product and sum rounded,
+ * instead of the k-ascending FMA chain.  (`K^-1 @ grid`, stn.py:47, keeps the FMA chain because
+ * torch.inverse returns K^-1 column-major; profiles/r01_probe_bmm*.json, r01_probe_b1_calls.json.)
+ * Set by the Python layer when the reference would have issued such a call. */
 #define TCSFM_ARITH_BMM_NOFMA  (1 << 6)
 /* pair-loss configuration (losses.py:65-73,151-183 config keys) */
 #define TCSFM_AUTO_MASK        (1 << 1)   /* with_auto_mask   */

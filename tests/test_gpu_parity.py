@@ -366,3 +366,43 @@ def test_pft_window_runner_reuses_graphs():
         ref = pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts, iterations=3)
         assert torch.allclose(got["losses"], ref["losses"], rtol=1e-4, atol=0), (seed, got["losses"], ref["losses"])
         assert (got["disparity"] - ref["disparity"]).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_randomised_sweep_vs_eager_cuda(seed):
+    """Random shapes (not multiples of the 64x16 tile), intrinsics, poses (up to ~10 deg and large
+    translations: wide out-of-view bands, points behind the camera), depth ranges and batch sizes:
+    every forward output bit for bit, gradients (incl. the sampled image's) within 1e-4."""
+    gen = torch.Generator().manual_seed(1234 + seed)
+    b = int(torch.randint(1, 5, (1,), generator=gen))
+    h = int(torch.randint(18, 200, (1,), generator=gen))
+    w = int(torch.randint(18, 300, (1,), generator=gen))
+    fr = synth.make_frames(b, h, w, seed=100 + seed, yaw=0.02, device=DEV, intrinsics=synth.scaled_intrinsics(h, w))
+    K = fr["K"].clone()
+    K[:, 0, 0] *= float(0.6 + 0.8 * torch.rand(1, generator=gen))
+    K[:, 1, 1] *= float(0.6 + 0.8 * torch.rand(1, generator=gen))
+    K[:, 0, 1] = float(2.0 * torch.rand(1, generator=gen))                     # skew: K^-1 without exact zeros
+    scale = torch.tensor([0.05, 0.05, 0.3, 0.05, 0.18, 0.05])
+    pose = (torch.randn(b, 6, generator=gen) * scale).to(DEV)
+    if seed % 3 == 0:
+        pose[:, 2] = -3.0                                                       # many points behind the camera
+    depth_scale = float(0.2 + 3.0 * torch.rand(1, generator=gen))
+    src = leaf(fr["sources"][0])
+    up = [torch.randn(b, c, h, w, device=DEV) for c in (3, 1, 1)]
+    res = []
+    for fn in (O.inverse_warp2, stn.inverse_warp2):
+        s_ = leaf(src)
+        d0, d1, p0 = leaf(fr["depths"][0] * depth_scale), leaf(fr["depths"][1] * depth_scale), leaf(pose)
+        pim, vm, pd, cd = fn(s_, d0, d1, p0, K, 'zeros')
+        ((pim * up[0]).sum() + (pd * up[1]).sum() + (cd * up[2]).sum()).backward()
+        res.append((pim, vm, pd, cd, d0.grad, d1.grad, p0.grad, s_.grad))
+    ref, got = res
+    for i in range(4):
+        assert torch.equal(got[i], ref[i]), (seed, i, int((got[i] != ref[i]).sum()))
+    for i in range(4, 8):
+        assert rel_l2(got[i], ref[i]) < 1e-4, (seed, i, rel_l2(got[i], ref[i]))
+    cfg = goldens.FULL_CFG if seed % 2 else goldens.TRAIN_CFG
+    args = (fr["target"], fr["sources"][0], fr["depths"][0] * depth_scale, fr["depths"][1] * depth_scale, pose, K)
+    pr = O.pairwise_loss(cfg, *args)
+    pg = losses.Compute_Loss(cfg).compute_pairwise_loss(*args, 5)
+    assert torch.equal(pg[3], pr[3]) and torch.equal(pg[2], pr[2]), (seed, int((pg[3] != pr[3]).sum()))
