@@ -228,3 +228,21 @@ def test_smooth_loss_vs_oracle(emu_ops, shape):
     (ref * 1.7).backward()
     (got * 1.7).backward()
     assert rel_l2(d_got.grad, d_ref.grad) < 1e-4
+
+
+def test_l1_only_configuration_matches_oracle(emu_ops):
+    """l_ssim=False (no reference script uses it): diff_img keeps 3 channels; composed path."""
+    from oracle import ref_torch as O
+    g = Golden(goldens.CASES[0])
+    fr = g.frames()
+    cfg = dict(goldens.FULL_CFG, l_ssim=False)
+    d0 = leaf(fr["depths"][0])
+    got = losses.Compute_Loss(cfg).compute_pairwise_loss(fr["target"], fr["sources"][0], d0, fr["depths"][1],
+                                                         -fr["poses"][0], fr["K"], 5)
+    d0r = leaf(fr["depths"][0])
+    ref = O.pairwise_loss(cfg, fr["target"], fr["sources"][0], d0r, fr["depths"][1], -fr["poses"][0], fr["K"])
+    assert got[2].shape == ref[2].shape and got[2].shape[1] == 3
+    assert torch.equal(got[3], ref[3]) and (got[2] - ref[2]).abs().max() < 1e-6
+    (got[2].sum() + got[0]).backward()
+    (ref[2].sum() + ref[0]).backward()
+    assert rel_l2(d0.grad, d0r.grad) < 1e-4

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi, ops
-from .stn import inverse_intrinsics, pose_vec2mat
+from .stn import inverse_intrinsics, inverse_warp2, pose_vec2mat
 
 
 class SSIM_Loss(nn.Module):
@@ -80,8 +80,9 @@ class Compute_Loss(nn.modules.Module):
         if intrinsics.requires_grad:
             raise NotImplementedError("gradients w.r.t. the intrinsics are not implemented")
         if self.config['l_ssim'] != True:   # noqa: E712
-            raise NotImplementedError("the fused pair loss implements the l_ssim=True configuration "
-                                      "(the default of every reference script)")
+            # L1-only configuration (diff_img keeps its 3 channels, losses.py:154,180): composed from the
+            # fused warp; no reference script runs it, so it gets no dedicated kernel
+            return [self._pairwise_l1_only(*s, intrinsics) for s in specs]
         n = len(specs)
         kinv = inverse_intrinsics(intrinsics)                        # models/stn.py:257
         if intrinsics.shape[0] == 1:
@@ -97,6 +98,18 @@ class Compute_Loss(nn.modules.Module):
         diff, mask, l_rep, l_dep = ops.PairLossFn.apply(cfg, n, kinv, proj, *tensors)
         want_depth = self.config['l_depth_consist'] == True          # noqa: E712
         return [(l_rep[i], l_dep[i] if want_depth else 0, diff[i], mask[i]) for i in range(n)]
+
+    def _pairwise_l1_only(self, tgt_img, ref_img, tgt_depth, ref_depth, pose, intrinsics):
+        warped, valid_mask, projected_depth, computed_depth = inverse_warp2(ref_img, tgt_depth, ref_depth, pose, intrinsics)
+        diff_img = (tgt_img - warped).abs().clamp(0, 1)
+        if self.config['with_auto_mask'] == True:   # noqa: E712
+            valid_mask = (diff_img.mean(dim=1, keepdim=True)
+                          < (tgt_img - ref_img).abs().mean(dim=1, keepdim=True)).float() * valid_mask
+        diff_depth = ((computed_depth - projected_depth).abs() / (computed_depth + projected_depth)).clamp(0, 1)
+        if self.config['with_depth_mask']:
+            diff_img = diff_img * (1 - diff_depth)
+        l_depth = self.mean_on_mask(diff_depth, valid_mask) if self.config['l_depth_consist'] == True else 0   # noqa: E712
+        return self.mean_on_mask(diff_img, valid_mask), l_depth, diff_img, valid_mask
 
     def _can_fuse_frame(self, specs, intrinsics):
         return (self.config['l_ssim'] == True and not intrinsics.requires_grad      # noqa: E712
