@@ -61,45 +61,6 @@ __device__ __forceinline__ PairCtx make_ctx(const tcsfm_pair_group& g, int b, in
     return c;
 }
 
-// Tap addressing shared by every plane sampled at one warped point.
-struct TapIdx {
-    int off;                       // y0 * W + x0 (may be out of range when a predicate is false)
-    bool nw, ne, sw, se;           // tap inside the image
-    float w_nw, w_ne, w_sw, w_se;  // bilinear weights, products rounded like ATen
-};
-
-__device__ __forceinline__ TapIdx make_taps(const WarpPt& p, int H, int W) {
-    TapIdx t;
-    const bool x0in = (p.x0 >= 0) && (p.x0 < W), x1in = (p.x0 >= -1) && (p.x0 < W - 1);
-    const bool y0in = (p.y0 >= 0) && (p.y0 < H), y1in = (p.y0 >= -1) && (p.y0 < H - 1);
-    t.off = p.y0 * W + p.x0;
-    t.nw = y0in && x0in; t.ne = y0in && x1in; t.sw = y1in && x0in; t.se = y1in && x1in;
-    t.w_nw = __fmul_rn(p.wx0, p.wy0);
-    t.w_ne = __fmul_rn(p.wx1, p.wy0);
-    t.w_sw = __fmul_rn(p.wx0, p.wy1);
-    t.w_se = __fmul_rn(p.wx1, p.wy1);
-    return t;
-}
-
-__device__ __forceinline__ Taps load_taps(const float* __restrict__ plane, const TapIdx& t, int W) {
-    Taps v;
-    const float* r0 = plane + t.off;
-    v.nw = t.nw ? __ldg(r0) : 0.f;
-    v.ne = t.ne ? __ldg(r0 + 1) : 0.f;
-    v.sw = t.sw ? __ldg(r0 + W) : 0.f;
-    v.se = t.se ? __ldg(r0 + W + 1) : 0.f;
-    return v;
-}
-
-// grid_sampler_2d bilinear accumulate: out = 0; out = fma(v, w, out) in nw, ne, sw, se order
-__device__ __forceinline__ float blend(const Taps& v, const TapIdx& t) {
-    float acc = __fmul_rn(v.nw, t.w_nw);
-    acc = __fmaf_rn(v.ne, t.w_ne, acc);
-    acc = __fmaf_rn(v.sw, t.w_sw, acc);
-    acc = __fmaf_rn(v.se, t.w_se, acc);
-    return acc;
-}
-
 // Fills one shared-memory cell with (target, warped source) of the image pixel (rx, ry).
 template <int F>
 __device__ __forceinline__ void fill_cell(const PairCtx& c, const Cam& cam, const Arith& A, int rx, int ry,

@@ -10,6 +10,7 @@
 namespace tcsfm {
 
 constexpr int kWarpThreads = 256;
+constexpr int kWarpBwdPix = 4;
 
 template <int F>
 __global__ void __launch_bounds__(kWarpThreads)
@@ -28,10 +29,11 @@ warp_fwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
     const int64_t o = (int64_t)b * n + pix;
     WarpPt p;
     warp_point<F>(c, A, u, v, __ldg(depth + o), p);
+    const TapIdx ti = make_taps(p, A.H, A.W);
     if (out_img || out_stack) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-            const float w = sample_plane(img + b * img_sb + ch * img_sc, p, A.H, A.W);
+            const float w = blend(load_taps(img + b * img_sb + ch * img_sc, ti, A.W), ti);
             if (out_img) out_img[((int64_t)b * 3 + ch) * n + pix] = w;
             if (out_stack) {          // next pose-net input: [target * valid | reconstruction], train_mono.py:74-76
                 out_stack[((int64_t)b * 6 + 3 + ch) * n + pix] = w;
@@ -40,22 +42,20 @@ warp_fwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
         }
     }
     if (out_valid) out_valid[o] = p.valid ? 1.f : 0.f;
-    if (out_pd) out_pd[o] = sample_plane(ref_depth + (int64_t)b * n, p, A.H, A.W);
+    if (out_pd) out_pd[o] = blend(load_taps(ref_depth + (int64_t)b * n, ti, A.W), ti);
     if (out_cd) out_cd[o] = p.Z;
 }
 
-__device__ __forceinline__ void scatter_taps(float* __restrict__ plane, const WarpPt& p, float g, int H, int W) {
-    const bool x0in = (p.x0 >= 0) && (p.x0 < W), x1in = (p.x0 + 1 >= 0) && (p.x0 + 1 < W);
-    const bool y0in = (p.y0 >= 0) && (p.y0 < H), y1in = (p.y0 + 1 >= 0) && (p.y0 + 1 < H);
-    float* r0 = plane + (int64_t)p.y0 * W + p.x0;
-    if (y0in && x0in) atomicAdd(r0, g * (p.wx0 * p.wy0));
-    if (y0in && x1in) atomicAdd(r0 + 1, g * (p.wx1 * p.wy0));
-    if (y1in && x0in) atomicAdd(r0 + W, g * (p.wx0 * p.wy1));
-    if (y1in && x1in) atomicAdd(r0 + W + 1, g * (p.wx1 * p.wy1));
+__device__ __forceinline__ void scatter_taps(float* __restrict__ plane, const TapIdx& t, float g, int W) {
+    float* r0 = plane + t.off;
+    if (t.nw) atomicAdd(r0, g * t.w_nw);
+    if (t.ne) atomicAdd(r0 + 1, g * t.w_ne);
+    if (t.sw) atomicAdd(r0 + W, g * t.w_sw);
+    if (t.se) atomicAdd(r0 + W + 1, g * t.w_se);
 }
 
 template <int F>
-__global__ void __launch_bounds__(kWarpThreads)
+__global__ void __launch_bounds__(kWarpThreads, 3)
 warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
                 const float* __restrict__ depth, const float* __restrict__ ref_depth,
                 const float* __restrict__ kinv, const float* __restrict__ proj,
@@ -66,42 +66,46 @@ warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
     TCSFM_SHARED float red[12 * (kWarpThreads / 32)];
     const int b = blockIdx.y;
     const int n = A.H * A.W;
-    const int pix = blockIdx.x * kWarpThreads + threadIdx.x;
     float acc[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) acc[i] = 0.f;
-    if (pix < n) {
-        const Cam c = load_cam(kinv, proj, b);
+    const Cam c = load_cam(kinv, proj, b);
+    // kWarpBwdPix pixels per thread: the 12-value block reduction and the camera loads are amortised
+#pragma unroll 1
+    for (int k = 0; k < kWarpBwdPix; ++k) {
+        const int pix = (blockIdx.x * kWarpBwdPix + k) * kWarpThreads + threadIdx.x;
+        if (pix >= n) break;
         const int v = pix / A.W, u = pix - v * A.W;
         const int64_t o = (int64_t)b * n + pix;
         WarpPt p;
         warp_point<F>(c, A, u, v, __ldg(depth + o), p);
+        const TapIdx ti = make_taps(p, A.H, A.W);
         float g_ix = 0.f, g_iy = 0.f;
         if (g_oimg || g_ostack) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 float g = g_oimg ? __ldg(g_oimg + ((int64_t)b * 3 + ch) * n + pix) : 0.f;
                 if (g_ostack) g += __ldg(g_ostack + ((int64_t)b * 6 + 3 + ch) * n + pix);
-                const Taps t = gather_taps(img + b * img_sb + ch * img_sc, p, A.H, A.W);
+                const Taps t = load_taps(img + b * img_sb + ch * img_sc, ti, A.W);
                 bilinear_grad(t, p, g, g_ix, g_iy);
-                if (g_img) scatter_taps(g_img + ((int64_t)b * 3 + ch) * n, p, g, A.H, A.W);
+                if (g_img) scatter_taps(g_img + ((int64_t)b * 3 + ch) * n, ti, g, A.W);
             }
         }
         if (g_opd) {
             const float g = __ldg(g_opd + o);
-            const Taps t = gather_taps(ref_depth + (int64_t)b * n, p, A.H, A.W);
+            const Taps t = load_taps(ref_depth + (int64_t)b * n, ti, A.W);
             bilinear_grad(t, p, g, g_ix, g_iy);
-            if (g_ref_depth) scatter_taps(g_ref_depth + (int64_t)b * n, p, g, A.H, A.W);
+            if (g_ref_depth) scatter_taps(g_ref_depth + (int64_t)b * n, ti, g, A.W);
         }
         const float g_Z = g_ocd ? __ldg(g_ocd + o) : 0.f;
         const GeomGrad gg = geom_adjoint(c, A, p, g_ix, g_iy, g_Z);
         if (g_depth) g_depth[o] = gg.g_depth;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            acc[i * 4 + 0] = gg.gp[i] * p.cam[0];
-            acc[i * 4 + 1] = gg.gp[i] * p.cam[1];
-            acc[i * 4 + 2] = gg.gp[i] * p.cam[2];
-            acc[i * 4 + 3] = gg.gp[i];
+            acc[i * 4 + 0] += gg.gp[i] * p.cam[0];
+            acc[i * 4 + 1] += gg.gp[i] * p.cam[1];
+            acc[i * 4 + 2] += gg.gp[i] * p.cam[2];
+            acc[i * 4 + 3] += gg.gp[i];
         }
     }
     if (g_proj) block_atomic_accumulate<12>(acc, red, g_proj + b * 12, threadIdx.x, kWarpThreads);
@@ -146,7 +150,8 @@ extern "C" int tcsfm_warp_bwd(const float* img, int64_t img_sb, int64_t img_sc,
     if (g_ref_depth) cudaMemsetAsync(g_ref_depth, 0, plane, (cudaStream_t)stream);
     if (g_proj) cudaMemsetAsync(g_proj, 0, (size_t)B * 12 * sizeof(float), (cudaStream_t)stream);
     if (g_img) cudaMemsetAsync(g_img, 0, 3 * plane, (cudaStream_t)stream);
-    dim3 grid((H * W + kWarpThreads - 1) / kWarpThreads, B), block(kWarpThreads);
+    const int per_block = kWarpThreads * kWarpBwdPix;
+    dim3 grid((H * W + per_block - 1) / per_block, B), block(kWarpThreads);
     TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(warp_bwd_kernel<F>, grid, block, 0, stream, img, img_sb, img_sc, depth,
                                                ref_depth, kinv, proj, g_out_img, g_out_proj_depth, g_out_comp_depth, g_out_stack,
                                                g_depth, g_ref_depth, g_proj, g_img, A));
