@@ -295,19 +295,78 @@ def main_pft(args):
                                    "kernels": ksum}}))
 
 
+def main_sweep(args):
+    """Config 1's forward-only part: the loss-surface sweeps of the demo (plot_loss_surface.py:11-87 via
+    helpers.compute_photometric_error): batch-1 evaluations of warp + photometric error for a line of
+    translation and a line of yaw perturbations.  A launch-latency-bound use of the same kernels."""
+    from tcsfm_b200 import pft, synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.sweep_evals
+    if args.impl == "reference":
+        from oracle import ref_torch as O
+        dev, fn = "cpu", O.photometric_error
+        torch.set_num_threads(os.cpu_count() or 1)
+        n = min(n, 20)
+    else:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dev, fn = "cuda", pft.compute_photometric_error
+    fr = synth.make_frames(1, 192, 640, n_src=2, seed=0, device=dev, intrinsics=torch.tensor(synth.KITTI_K))
+    deltas = torch.linspace(-0.05, 0.05, n)
+
+    def sweep():
+        vals = []
+        with torch.no_grad():
+            for axis in (2, 4):                                 # forward translation, yaw
+                for d in deltas:
+                    pose = fr["poses"][0].clone()
+                    pose[:, axis] += d
+                    r = fn(fr["target"], fr["sources"][0], fr["depths"][0], fr["depths"][1], pose, fr["K"])
+                    vals.append((r["diff_img"] * r["valid_mask"] * r["weight_mask"]).sum() / r["valid_mask"].sum())
+        return torch.stack(vals)
+
+    sweep()
+    if dev == "cuda":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = sweep()
+    host = out.cpu()
+    dt = time.perf_counter() - t0
+    line = {"metric": "loss-surface evaluations/s (B=1, 192x640, forward only)", "value": 2 * n / dt, "unit": "evals/s",
+            "n_gpus": 1, "steps": 2 * n, "warmup": 2 * n, "ms_per_step": dt / (2 * n) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "demo_loss_surface_sweep_b1_192x640", "launch": "eager, wall clock incl. the final D2H"},
+            "e2e": {"value": 2 * n / dt, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4}}
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": line["value"], "unit": "evals/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "%d evaluations" % (2 * n)}
+    else:
+        line["surface_min"] = float(host.min())
+    emit(line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS) + sorted(PFT_WORKLOADS))
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS) + sorted(PFT_WORKLOADS) + ["sweep"])
     ap.add_argument("--cpu-steps", type=int, default=None, help="steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of replaying CUDA graphs")
+    ap.add_argument("--ddp-allreduce-mb", type=float, default=0.0,
+                    help="multi-GPU only: after every step all-reduce a buffer of this many MB over NCCL, standing in "
+                         "for DDP's exchange of the network gradients (62.9 MB for the reference's nets, SURVEY.md §5); "
+                         "the loss path itself has no collective.  Implies eager launches.")
+    ap.add_argument("--sweep-evals", type=int, default=100, help="workload 'sweep': evaluations per surface")
     args = ap.parse_args()
     if args.workload in PFT_WORKLOADS:
         return main_pft(args)
+    if args.workload == "sweep":
+        return main_sweep(args)
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -377,6 +436,11 @@ def main():
     # host-side control flow: the mean-on-mask threshold is decided on the device), so the
     # timed region contains exactly the device work of K full steps.
     graphs = None
+    grad_buf = None
+    if args.ddp_allreduce_mb > 0 and dist is not None:
+        grad_buf = torch.zeros(int(args.ddp_allreduce_mb * 1e6 / 4), device=dev)
+        args.no_graph = True
+        config["collective"] = "NCCL all-reduce of %.1f MB per step (DDP stand-in)" % args.ddp_allreduce_mb
     if not args.no_graph:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -401,6 +465,8 @@ def main():
             graphs[i % N_INPUT_SETS][0].replay()
         else:
             run_step(loss_mod, sets[i % N_INPUT_SETS], n_src)
+            if grad_buf is not None:
+                dist.all_reduce(grad_buf)
 
     # End-to-end arm: every step copies its inputs from pinned host memory and reads the loss
     # back to the host.  Two device-side input buffers are used so that the copy of step i+1
