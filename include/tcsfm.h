@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 4
+#define TCSFM_ABI_VERSION 5
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -164,9 +164,11 @@ int tcsfm_smooth_bwd(const float* disp, const float* img, int64_t img_sb, int64_
 /* ---- glue of Compute_Loss.forward (losses.py:75-140) ----------------------------
  * pose [N,6] (times `sign`; every call site passes -pose) -> K @ [Rx Ry Rz | t] as [N,12]
  * (models/stn.py:81-116,143-158,262); row i uses K[i % Bk].  Bit-identical to the eager
- * CUDA operators for N >= 2 (the batched k=3 SGEMM accumulation order).  The backward maps
- * grad(K[R|t]) to the 6-DoF pose gradient. */
-int tcsfm_pose_proj_fwd(const float* pose, float sign, const float* K, int Bk, float* proj, int N, void* stream);
+ * CUDA operators: the k-ascending FMA chain of the batched SGEMM when the reference's calls
+ * have batch >= 2, the non-fused batch-1 kernel with TCSFM_ARITH_BMM_NOFMA in `flags`.  The
+ * backward maps grad(K[R|t]) to the 6-DoF pose gradient. */
+int tcsfm_pose_proj_fwd(const float* pose, float sign, const float* K, int Bk, float* proj, int N, int flags,
+                        void* stream);
 int tcsfm_pose_proj_bwd(const float* pose, float sign, const float* K, int Bk, const float* g_proj,
                         float* g_pose, int N, void* stream);
 

@@ -177,7 +177,7 @@ def test_pose_proj_fwd_bwd_vs_torch():
     pose = (0.2 * torch.randn(12, 6, generator=gen)).requires_grad_(True)
     K = torch.tensor(synth.KITTI_K).repeat(4, 1, 1) + 0.01 * torch.rand(4, 3, 3, generator=gen)
     ref = K.repeat(3, 1, 1) @ stn.pose_vec2mat(-pose)
-    got = _raw.pose_proj_fwd(emu(), pose.detach(), K, -1.0)
+    got = _raw.pose_proj_fwd(emu(), pose.detach(), K, -1.0, 0)
     assert (got - ref).abs().max() < 1e-4 * ref.abs().max()
     gp = torch.randn(12, 3, 4, generator=gen)
     ref.backward(gp)

@@ -240,12 +240,12 @@ def test_pose_proj_bit_exact_vs_eager_cuda():
     bit for bit on the same GPU (sinf/cosf of the CUDA math library, k-ascending FMA chains)."""
     from tcsfm_b200 import _raw
     gen = torch.Generator().manual_seed(0)
-    for n, bk in ((32, 8), (2, 2), (24, 6), (4096, 8)):
+    for n, bk in ((32, 8), (2, 2), (24, 6), (4096, 8), (1, 1)):
         pose = (0.3 * torch.randn(n, 6, generator=gen)).to(DEV)
         pose[0, 3:] = 0.0
         K = (torch.tensor(synth.KITTI_K).repeat(bk, 1, 1) + 0.01 * torch.rand(bk, 3, 3, generator=gen)).to(DEV)
         ref = K.repeat(n // bk, 1, 1) @ stn.pose_vec2mat(-pose)
-        got = _raw.pose_proj_fwd(_lib.lib(), pose, K, -1.0)
+        got = _raw.pose_proj_fwd(_lib.lib(), pose, K, -1.0, ops.pose_flags(n))
         assert torch.equal(got, ref), (n, int((got != ref).sum()))
         p = leaf(pose)
         gp = torch.randn(n, 3, 4, device=DEV)

@@ -2,7 +2,7 @@
 package loader and by the test-only emulator binding)."""
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ARITH_CPU = 1 << 0
 AUTO_MASK = 1 << 1
@@ -56,7 +56,7 @@ SIGNATURES = {
                                   C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "tcsfm_smooth_fwd": (C.c_int, [_fp, _fp, _i64, _i64, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tcsfm_smooth_bwd": (C.c_int, [_fp, _fp, _i64, _i64, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "tcsfm_pose_proj_fwd": (C.c_int, [_fp, C.c_float, _fp, C.c_int, _fp, C.c_int, C.c_void_p]),
+    "tcsfm_pose_proj_fwd": (C.c_int, [_fp, C.c_float, _fp, C.c_int, _fp, C.c_int, C.c_int, C.c_void_p]),
     "tcsfm_pose_proj_bwd": (C.c_int, [_fp, C.c_float, _fp, C.c_int, _fp, _fp, C.c_int, C.c_void_p]),
     "tcsfm_disp_to_depth_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, _i64,
                                           C.c_float, C.c_float, C.c_void_p]),

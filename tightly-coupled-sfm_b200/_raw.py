@@ -196,13 +196,13 @@ def pair_loss_bwd(lib, batch, mask, sums, coef, g_diff, g_scalars, w_l1, w_ssim,
 # glue kernels of Compute_Loss.forward (csrc/frame_kernels.cu)
 # ---------------------------------------------------------------------------
 
-def pose_proj_fwd(lib, pose, K, sign):
+def pose_proj_fwd(lib, pose, K, sign, flags=0):
     """pose [N,6], K [Bk,3,3] -> K @ [R|t] as [N,3,4] (row i uses K[i % Bk])."""
     pose, K = _f32c(pose, "pose"), _f32c(K, "K")
     n = pose.shape[0]
     proj = torch.empty((n, 3, 4), dtype=torch.float32, device=pose.device)
     with _timing.launch("pose_proj_fwd", pose.is_cuda):
-        rc = lib.tcsfm_pose_proj_fwd(_ptr(pose), sign, _ptr(K), K.shape[0], _ptr(proj), n, _stream(pose))
+        rc = lib.tcsfm_pose_proj_fwd(_ptr(pose), sign, _ptr(K), K.shape[0], _ptr(proj), n, flags, _stream(pose))
     _cabi.check(lib, rc)
     _timing.count_launch()
     return proj

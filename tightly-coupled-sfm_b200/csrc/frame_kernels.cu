@@ -13,14 +13,17 @@
 
 namespace tcsfm {
 
-// 3x3 @ 3xN product with the k-ascending FMA chain of the batched SGEMM (see dot3_blas).
-template <int N>
+// 3x3 @ 3xN product in the rounding order of eager torch.bmm: the k-ascending FMA chain of the
+// batched SGEMM for batch >= 2, products and sums rounded separately for batch 1 (see dot3_*).
+template <int N, bool kNoFma>
 __device__ __forceinline__ void matmul3(const float* a, const float* b, float* out) {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < N; ++j)
-            out[i * N + j] = dot3_blas(a[i * 3 + 0], a[i * 3 + 1], a[i * 3 + 2], b[0 * N + j], b[1 * N + j], b[2 * N + j]);
+            out[i * N + j] = kNoFma
+                ? dot3_nofma(a[i * 3 + 0], a[i * 3 + 1], a[i * 3 + 2], b[0 * N + j], b[1 * N + j], b[2 * N + j])
+                : dot3_blas(a[i * 3 + 0], a[i * 3 + 1], a[i * 3 + 2], b[0 * N + j], b[1 * N + j], b[2 * N + j]);
 }
 
 struct Euler {
@@ -43,6 +46,7 @@ __device__ __forceinline__ Euler euler_matrices(float rx, float ry, float rz) {
     return e;
 }
 
+template <bool kNoFma>
 __global__ void pose_proj_fwd_kernel(const float* __restrict__ pose, float sign, const float* __restrict__ K, int Bk,
                                      float* __restrict__ proj, int N) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,8 +56,8 @@ __global__ void pose_proj_fwd_kernel(const float* __restrict__ pose, float sign,
     for (int j = 0; j < 6; ++j) p[j] = sign * pose[i * 6 + j];
     const Euler e = euler_matrices(p[3], p[4], p[5]);
     float XY[9], R[9], T[12], P[12], Km[9];
-    matmul3<3>(e.X, e.Y, XY);
-    matmul3<3>(XY, e.Z, R);
+    matmul3<3, kNoFma>(e.X, e.Y, XY);
+    matmul3<3, kNoFma>(XY, e.Z, R);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         T[r * 4 + 0] = R[r * 3 + 0]; T[r * 4 + 1] = R[r * 3 + 1]; T[r * 4 + 2] = R[r * 3 + 2];
@@ -61,7 +65,7 @@ __global__ void pose_proj_fwd_kernel(const float* __restrict__ pose, float sign,
     }
 #pragma unroll
     for (int j = 0; j < 9; ++j) Km[j] = K[(i % Bk) * 9 + j];
-    matmul3<4>(Km, T, P);
+    matmul3<4, kNoFma>(Km, T, P);
 #pragma unroll
     for (int j = 0; j < 12; ++j) proj[i * 12 + j] = P[j];
 }
@@ -191,9 +195,14 @@ __global__ void frame_bwd_prepare_kernel(const float* __restrict__ g_out, tcsfm_
 
 using namespace tcsfm;
 
-extern "C" int tcsfm_pose_proj_fwd(const float* pose, float sign, const float* K, int Bk, float* proj, int N, void* stream) {
+extern "C" int tcsfm_pose_proj_fwd(const float* pose, float sign, const float* K, int Bk, float* proj, int N, int flags,
+                                   void* stream) {
     if (!pose || !K || !proj || N <= 0 || Bk <= 0) { set_error("tcsfm_pose_proj_fwd: bad arguments"); return 1; }
-    TCSFM_LAUNCH(pose_proj_fwd_kernel, dim3((N + 63) / 64), dim3(64), 0, stream, pose, sign, K, Bk, proj, N);
+    if (flags & TCSFM_ARITH_BMM_NOFMA) {
+        TCSFM_LAUNCH(pose_proj_fwd_kernel<true>, dim3((N + 63) / 64), dim3(64), 0, stream, pose, sign, K, Bk, proj, N);
+    } else {
+        TCSFM_LAUNCH(pose_proj_fwd_kernel<false>, dim3((N + 63) / 64), dim3(64), 0, stream, pose, sign, K, Bk, proj, N);
+    }
     return check_launch("tcsfm_pose_proj_fwd");
 }
 

@@ -85,12 +85,12 @@ class Compute_Loss(nn.modules.Module):
             return [self._pairwise_l1_only(*s, intrinsics) for s in specs]
         n = len(specs)
         kinv = inverse_intrinsics(intrinsics)                        # models/stn.py:257
-        if intrinsics.shape[0] == 1:
-            # batch 1 runs a different (non-fused) cuBLAS kernel in the reference: issue the same calls
+        poses = torch.cat([s[4][:, 0:6] for s in specs], 0)              # [n*B, 6]
+        if poses.is_cuda:
+            # models/stn.py:259-262 for every pair in one launch (rounded like the reference's batch-B calls)
+            proj = ops.PoseProjFn.apply(poses, intrinsics, 1.0, intrinsics.shape[0])
+        else:   # only reachable from the CPU-emulated tests, whose fixtures carry the CPU's sin/cos bits
             proj = torch.cat([intrinsics @ pose_vec2mat(s[4][:, 0:6]) for s in specs], 0)
-        else:
-            poses = torch.cat([s[4][:, 0:6] for s in specs], 0)          # [n*B, 6]
-            proj = intrinsics.repeat(n, 1, 1) @ pose_vec2mat(poses)      # models/stn.py:259-262
         tensors = []
         for tgt_img, ref_img, tgt_depth, ref_depth, _ in specs:
             tensors += [tgt_img, ref_img, tgt_depth, ref_depth]
@@ -113,7 +113,7 @@ class Compute_Loss(nn.modules.Module):
 
     def _can_fuse_frame(self, specs, intrinsics):
         return (self.config['l_ssim'] == True and not intrinsics.requires_grad      # noqa: E712
-                and len(specs) <= 8 and intrinsics.shape[0] >= 2
+                and len(specs) <= 8
                 and all(s[0].shape == specs[0][0].shape and s[1].shape == specs[0][0].shape for s in specs))
 
     def _frame_terms(self, specs, roles, intrinsics):

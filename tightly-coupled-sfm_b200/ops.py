@@ -26,6 +26,14 @@ def arith_flags(batch, height, width):
     return flags
 
 
+def pose_flags(ref_batch):
+    """The 3x3 products of the pose algebra (m*n*k <= 36) always take the non-fused cuBLAS kernel
+    at batch 1 (tools/probe_b1_pose.py)."""
+    if not (ARITH_FLAGS & _cabi.ARITH_CPU) and ref_batch == 1:
+        return _cabi.ARITH_BMM_NOFMA
+    return 0
+
+
 def _guard(t):
     """Makes the tensor's GPU current for the launch (the C ABI launches on the
     current device / the stream it is handed)."""
@@ -145,10 +153,13 @@ class PoseProjFn(torch.autograd.Function):
     (csrc/frame_kernels.cu); one launch forward, one backward."""
 
     @staticmethod
-    def forward(ctx, pose, K, sign):
+    def forward(ctx, pose, K, sign, ref_batch=None):
+        # ref_batch: batch size of the reference's own `intrinsics @ pose_vec2mat(pose)` calls this
+        # launch stands in for (cuBLAS rounds batch-1 products differently)
         _require_cuda(pose, K)
+        flags = pose_flags(pose.shape[0] if ref_batch is None else ref_batch)
         with _guard(pose):
-            proj = _raw.pose_proj_fwd(lib(), pose, K, sign)
+            proj = _raw.pose_proj_fwd(lib(), pose, K, sign, flags)
         ctx.save_for_backward(pose, K)
         ctx.sign = sign
         return proj
@@ -158,7 +169,7 @@ class PoseProjFn(torch.autograd.Function):
         pose, K = ctx.saved_tensors
         with _guard(pose):
             g_pose = _raw.pose_proj_bwd(lib(), pose, K, ctx.sign, g_proj)
-        return g_pose, None, None
+        return g_pose, None, None, None
 
 
 class FrameLossFn(torch.autograd.Function):
@@ -187,7 +198,7 @@ class FrameLossFn(torch.autograd.Function):
             for i in range(0, len(disps), 4):
                 depths += _raw.disp_to_depth_fwd(lib(), disps[i:i + 4], min_disp, max_disp - min_disp)
             poses = torch.cat([p[:, 0:6] for p in poses_in], 0)
-            proj = _raw.pose_proj_fwd(lib(), poses, K, -1.0)
+            proj = _raw.pose_proj_fwd(lib(), poses, K, -1.0, pose_flags(b))
             specs = [{"tgt_img": images[ti], "ref_img": images[ri], "tgt_depth": depths[td], "ref_depth": depths[rd],
                       "kinv": kinv, "proj": proj[i * b:(i + 1) * b]} for i, (_, ti, ri, td, rd) in enumerate(groups)]
             batch = _raw.PairBatch(specs)

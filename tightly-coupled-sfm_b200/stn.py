@@ -94,13 +94,12 @@ def inverse_intrinsics(intrinsics):
 
 
 def projection_matrices(pose, intrinsics, kinv=None):
-    """(K^-1, K @ [R|t]) as models/stn.py:257-262 forms them.  On the GPU with a batch of at
-    least two poses the 25-kernel euler/bmm chain is one fused launch that reproduces it bit for
-    bit (csrc/frame_kernels.cu); batch 1 takes the eager operators because cuBLAS switches to a
-    differently rounded kernel there."""
+    """(K^-1, K @ [R|t]) as models/stn.py:257-262 forms them.  On the GPU the 25-kernel euler/bmm
+    chain is one fused launch that reproduces it bit for bit (csrc/frame_kernels.cu), including
+    the differently rounded cuBLAS kernel eager PyTorch uses at batch 1."""
     if kinv is None:
         kinv = inverse_intrinsics(intrinsics)
-    if pose.is_cuda and pose.shape[0] >= 2 and not intrinsics.requires_grad:
+    if pose.is_cuda and not intrinsics.requires_grad:
         return kinv, ops.PoseProjFn.apply(pose[:, 0:6], intrinsics, 1.0)
     return kinv, intrinsics @ pose_vec2mat(pose[:, 0:6])
 
