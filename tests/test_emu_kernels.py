@@ -192,3 +192,42 @@ def test_min_reduce_and_routing_ties():
     ref = torch.min(stack.permute(1, 0, 2, 3, 4).reshape(2, 3, 9, 11), 1)[0].sum()
     got = _raw.min_reduce(emu(), stack[0], stack[0].numel(), 3, stack[0].numel())
     assert abs(float(got) - float(ref)) < 1e-4
+
+
+@pytest.mark.parametrize("hw", [(2, 2), (3, 3), (2, 70), (5, 66), (17, 3), (16, 64), (33, 129)])
+def test_pair_and_photo_tiny_and_edge_sizes_vs_oracle(hw):
+    """Degenerate / tile-edge image sizes: reflection padding with H or W of 2-3, exactly one tile,
+    one pixel past a tile.  Forward bit for bit, gradients within tolerance, against the oracle."""
+    h, w = hw
+    fr = synth.make_frames(2, h, w, seed=h * 7 + w, intrinsics=synth.scaled_intrinsics(max(h, 8), max(w, 8)))
+    cfg = goldens.FULL_CFG
+    flags = cfg_flags(cfg)
+    pose = -fr["poses"][0]
+    kinv, proj = stn.projection_matrices(pose, fr["K"])
+    batch = _raw.PairBatch([{"tgt_img": fr["target"], "ref_img": fr["sources"][0], "tgt_depth": fr["depths"][0],
+                             "ref_depth": fr["depths"][1], "kinv": kinv, "proj": proj}])
+    diff, mask, sums, coef = _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, flags)
+    td, rd = fr["depths"][0].clone().requires_grad_(True), fr["depths"][1].clone().requires_grad_(True)
+    _, _, rdiff, rmask, _ = O.pairwise_loss(cfg, fr["target"], fr["sources"][0], td, rd, pose, fr["K"])
+    # (with fewer than ~16 pixels the CPU BLAS behind the oracle's k=3 bmm rounds differently, so the
+    # degenerate sizes are compared to 1e-4 instead of bit for bit)
+    exact = h * w >= 16
+    assert same(mask[0], rmask)
+    assert same(diff[0], rdiff) if exact else (diff[0] - rdiff).abs().max() < 1e-4
+    gen = torch.Generator().manual_seed(1)
+    g_diff = torch.randn(1, 2, 1, h, w, generator=gen)
+    g_td, g_rd, _ = _raw.pair_loss_bwd(emu(), batch, mask, sums, coef, g_diff, None, 0.15, 0.85, flags, True)
+    (rdiff * g_diff[0]).sum().backward()
+    assert rel_l2(g_td[0], td.grad) < 1e-4 and rel_l2(g_rd[0], rd.grad) < 1e-4
+    # PFT photometric block on the same inputs
+    rec, _, pd, cd = _raw.warp_fwd(emu(), fr["sources"][0], fr["depths"][0], fr["depths"][1], kinv, proj, CPU)
+    six = torch.cat([fr["target"], fr["sources"][0]], 1)
+    rec_l = rec.clone().requires_grad_(True)
+    ref = O.pft_error_maps(six, rec_l, pd, cd)
+    got = _raw.photo_fwd(emu(), six[:, 0:3], six[:, 3:6], rec, pd, cd, 0.15, 0.85, CPU)
+    for a, b_ in zip(got[:4], ref):
+        assert same(a, b_) if exact else (a - b_).abs().max() < 1e-4
+    g1 = torch.randn(2, 1, h, w, generator=gen)
+    (ref[1] * g1).sum().backward()
+    g_rec, _, _ = _raw.photo_bwd(emu(), six[:, 0:3], rec, pd, cd, got[4], g1, None, 0.15, 0.85, CPU)
+    assert rel_l2(g_rec, rec_l.grad) < 1e-4
