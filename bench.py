@@ -362,6 +362,9 @@ def main():
                          "for DDP's exchange of the network gradients (62.9 MB for the reference's nets, SURVEY.md §5); "
                          "the loss path itself has no collective.  Implies eager launches.")
     ap.add_argument("--sweep-evals", type=int, default=100, help="workload 'sweep': evaluations per surface")
+    ap.add_argument("--profile", default="full", choices=["full", "train"],
+                    help="loss flags: 'full' = depth-consistency mask + term on (what PFT uses, 84 B/px/pair), "
+                         "'train' = the paper's training defaults (run_mono_training.py:50-64: both off)")
     args = ap.parse_args()
     if args.workload in PFT_WORKLOADS:
         return main_pft(args)
@@ -407,7 +410,11 @@ def main():
     from tcsfm_b200 import _timing, losses, synth
     kitti = wl["h"] in (192, 376)
     rng = synth.KITTI_DEPTH_RANGE if kitti else synth.SCANNET_DEPTH_RANGE
-    loss_mod = losses.Compute_Loss(dict(LOSS_CFG, num_scales=wl.get("scales", 1), min_depth=rng[0], max_depth=rng[1]))
+    flags_cfg = {} if args.profile == "full" else {"l_depth_consist": False, "with_depth_mask": False}
+    if args.profile == "train":
+        config["flags"] = "paper training defaults (auto-mask, SSIM+L1; no depth-consistency mask/term)"
+    loss_mod = losses.Compute_Loss(dict(LOSS_CFG, num_scales=wl.get("scales", 1), min_depth=rng[0], max_depth=rng[1],
+                                        **flags_cfg))
     n_src = wl["n_src"]
     sets = [make_inputs(wl, 100 * rank + s, dev) for s in range(N_INPUT_SETS)]
     host_sets = [make_inputs(wl, 100 * rank + s, dev, pin=True) for s in range(2)]
