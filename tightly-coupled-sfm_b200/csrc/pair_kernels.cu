@@ -35,6 +35,13 @@ namespace tcsfm {
 #define TCSFM_BWD_MIN_BLOCKS 4      // measured: 4 CTAs/SM with ~200 B of spills beats 2-3 CTAs/SM without (latency bound)
 #endif
 
+#ifndef TCSFM_BWD_MIN2
+#define TCSFM_BWD_MIN2 1
+#endif
+#ifndef TCSFM_BWD_STAGE_UNROLL
+#define TCSFM_BWD_STAGE_UNROLL 1
+#endif
+
 constexpr int kMaxGroups = 8;
 constexpr int kCoefPlanes = 10;      // 3 channels x (A, B, C) + the un-weighted photometric error
 
@@ -64,9 +71,9 @@ __device__ __forceinline__ PairCtx make_ctx(const tcsfm_pair_group& g, int b, in
 // Fills one shared-memory cell with (target, warped source) of the image pixel (rx, ry).
 template <int F>
 __device__ __forceinline__ void fill_cell(const PairCtx& c, const Cam& cam, const Arith& A, int rx, int ry,
-                                          float2* tw, int cells, int cell, WarpPt& p, TapIdx& ti) {
+                                          float depth, float2* tw, int cells, int cell, WarpPt& p, TapIdx& ti) {
     const int pix = ry * A.W + rx;
-    warp_point<F>(cam, A, rx, ry, __ldg(c.tdep + pix), p);
+    warp_point<F>(cam, A, rx, ry, depth, p);
     ti = make_taps(p, A.H, A.W);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
@@ -114,7 +121,24 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
     const int gx = x0 + tx;
 
     float own_mask[kPixPerThread], own_dd[kPixPerThread];
-    // ---- phase A: own pixels ----
+    // ---- phase A: own pixels.  The target depths head the longest dependent chain (depth ->
+    //      projection -> tap addresses -> gathers), so all of a thread's are requested first. ----
+    int src_x[kPixPerThread + 1], src_y[kPixPerThread + 1];
+    bool src_ok[kPixPerThread + 1];
+    float src_depth[kPixPerThread + 1];
+#pragma unroll
+    for (int k = 0; k <= kPixPerThread; ++k) {
+        int cell;
+        if (k < kPixPerThread) cell = T1::cell(tx, ty0 + k);
+        else {                                         // the thread's halo-ring cell, if it has one
+            int cx = 0, cy = 0;
+            ring_cell(threadIdx.x < kRingCells ? threadIdx.x : 0, cx, cy);
+            cell = T1::cell(cx, cy);
+        }
+        // cells of a partial tile that lie outside the image hold the reflected pixel (or zero)
+        src_ok[k] = T1::cell_to_reflected(cell, x0, y0, H, W, src_y[k], src_x[k]) && (k < kPixPerThread || threadIdx.x < kRingCells);
+        src_depth[k] = src_ok[k] ? __ldg(c.tdep + src_y[k] * W + src_x[k]) : 1.0f;
+    }
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
         const int gy = y0 + ty0 + k;
@@ -122,11 +146,8 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
         float m = 0.f, dd = 0.f;
         WarpPt p;
         TapIdx ti;
-        // cells of a partial tile that lie outside the image hold the reflected pixel (or zero)
         const bool own = gx < W && gy < H;
-        int rx = gx, ry = gy;
-        const bool ok = own || T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx);
-        if (ok) fill_cell<F>(c, cam, A, rx, ry, tw, T1::kCells, cell, p, ti);
+        if (src_ok[k]) fill_cell<F>(c, cam, A, src_x[k], src_y[k], src_depth[k], tw, T1::kCells, cell, p, ti);
         else zero_cell(tw, T1::kCells, cell);
         if (own) {
             m = p.valid ? 1.f : 0.f;
@@ -148,12 +169,12 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
     }
     // ---- phase A': the halo ring (one cell per thread) ----
     if (threadIdx.x < kRingCells) {
-        int cx, cy, ry, rx;
+        int cx, cy;
         ring_cell(threadIdx.x, cx, cy);
         const int cell = T1::cell(cx, cy);
         WarpPt p;
         TapIdx ti;
-        if (T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx)) fill_cell<F>(c, cam, A, rx, ry, tw, T1::kCells, cell, p, ti);
+        if (src_ok[kPixPerThread]) fill_cell<F>(c, cam, A, src_x[kPixPerThread], src_y[kPixPerThread], src_depth[kPixPerThread], tw, T1::kCells, cell, p, ti);
         else zero_cell(tw, T1::kCells, cell);
     }
     __syncthreads();
@@ -223,11 +244,12 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
 // ---------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------
-struct BwdScalars { float c_rep, c_dep; };
+struct BwdScalars { float c_rep, c_dep, g_min; };
 
 __device__ __forceinline__ BwdScalars bwd_scalars(const tcsfm_pair_group& g, bool depth_consist) {
     BwdScalars s;
     s.c_rep = 0.f; s.c_dep = 0.f;
+    s.g_min = g.min_base ? __ldg(g.g_min) : 0.f;
     if (g.g_scalars) {
         const float s1 = __ldg(g.sums + 1);
         if (s1 > 10000.0f) {                        // mean_on_mask, losses.py:144
@@ -248,14 +270,19 @@ __device__ __forceinline__ float upstream_diff(const tcsfm_pair_group& g, const 
         const float* mine = g.min_base + bn + pix;
         const float v = __ldg(mine + (int64_t)g.min_index * g.min_stride);
         bool win = true;
-        for (int j = 0; j < g.min_count; ++j) {
-            if (j == g.min_index) continue;
-            const float o = __ldg(mine + (int64_t)j * g.min_stride);
-            // torch.min(dim): the first index holding the minimum wins; a NaN is the minimum
-            if (j < g.min_index) win = win && !(o <= v || o != o);
-            else win = win && !(o < v || (o != o && v == v));
+        // torch.min(dim): the first index holding the minimum wins; a NaN is the minimum
+        if (TCSFM_BWD_MIN2 && g.min_count == 2) {                     // the usual two sources: branch-free, both loads in flight
+            const float o = __ldg(mine + (int64_t)(1 - g.min_index) * g.min_stride);
+            win = (g.min_index == 1) ? !(o <= v || o != o) : !(o < v || (o != o && v == v));
+        } else {
+            for (int j = 0; j < g.min_count; ++j) {
+                if (j == g.min_index) continue;
+                const float o = __ldg(mine + (int64_t)j * g.min_stride);
+                if (j < g.min_index) win = win && !(o <= v || o != o);
+                else win = win && !(o < v || (o != o && v == v));
+            }
         }
-        if (win) Gd += __ldg(g.g_min);
+        if (win) Gd += sc.g_min;
     }
     return Gd;
 }
@@ -264,7 +291,7 @@ template <int F>
 __global__ void __launch_bounds__(kTileThreads, TCSFM_BWD_MIN_BLOCKS)
 pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     using T1 = Tile<1>;
-    TCSFM_DYN_SMEM(float, cs);                     // [9][T1::kCells] upstream-scaled coefficients
+    TCSFM_DYN_SMEM(float, cs);                     // [9][T1::kCells] coefficients, [kCells] upstream, [own] depth upstream
     TCSFM_SHARED float red[12 * (kTileThreads / 32)];
 
     const tcsfm_pair_group& g = L.g[blockIdx.z];
@@ -292,7 +319,15 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     //      cp.async (no register staging, all loads in flight at once; zero fill outside the
     //      image), next to the upstream gradient of diff_img at each ring pixel ----
     float* Gs = cs + 9 * T1::kCells;               // [cells] upstream gradient (0 outside the image)
-    for (int cell = threadIdx.x; cell < T1::kCells; cell += kTileThreads) {
+    constexpr int kStageIters = (T1::kCells + kTileThreads - 1) / kTileThreads;
+#if TCSFM_BWD_STAGE_UNROLL
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+    for (int it = 0; it < kStageIters; ++it) {
+        const int cell = threadIdx.x + it * kTileThreads;
+        if (cell >= T1::kCells) break;
         int cx, cy;
         T1::cell_xy(cell, cx, cy);
         const int qx = x0 + cx, qy = y0 + cy;
@@ -300,7 +335,8 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         const int pix = inside ? qy * W + qx : 0;
         // coefficients only matter where the upstream gradient is non-zero (masked-out pixels of
         // the inverse groups, the losing source of the per-pixel min): skip their 36 B/px
-        const float Gd = inside ? upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, __ldg(mask + pix)) : 0.f;
+        const float m = inside ? __ldg(mask + pix) : 0.f;
+        const float Gd = inside ? upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, m) : 0.f;
         const bool live = Gd != 0.f;
 #pragma unroll
         for (int j = 0; j < 9; ++j)
@@ -311,37 +347,37 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     __pipeline_wait_prior(0);
     __syncthreads();
 
-    // ---- phases C + D, one own pixel at a time down the strip.
-    //      C: separable 3x3 sums of the nine coefficient planes with a rolling window of
-    //         horizontal 3-sums.  Reflection padding folds window taps that fall outside the
-    //         image back onto row/column 1 and H-2/W-2: those receive the border neighbour twice.
-    //      D: L1 / depth adjoints and the geometry adjoint. ----
-    float acc[12];
+    // ---- phase C: separable 3x3 sums of the nine coefficient planes down the strip with a
+    //      rolling window of horizontal 3-sums.  Reflection padding folds window taps that fall
+    //      outside the image back onto row/column 1 and H-2/W-2: those receive the border
+    //      neighbour twice.  Per channel the result is the gradient wrt the warped value as a
+    //      line in that value, g_w = P + w * Q; (P, Q) replace the coefficients of the own cells
+    //      in shared memory so that phase D starts with an empty register file. ----
+    {
+        float pq[kPixPerThread][6];
+        float h[3][9];
+        const bool dup_l = (gx == 1), dup_r = (gx == W - 2);
+        auto hsum = [&](int r, float (&out)[9]) {          // horizontal 3-sums of tile row ty0 - 1 + r
+            const int c1 = T1::cell(tx, ty0 - 1 + r);
+            // upstream of the three neighbours; a border neighbour that is folded back counts twice
+            const float gl = Gs[c1 - 1] * (dup_l ? 2.f : 1.f), gm = Gs[c1], gr = Gs[c1 + 1] * (dup_r ? 2.f : 1.f);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
-    float h[3][9];
-    const bool dup_l = (gx == 1), dup_r = (gx == W - 2);
-    auto hsum = [&](int r, float (&out)[9]) {          // horizontal 3-sums of tile row ty0 - 1 + r
-        const int c1 = T1::cell(tx, ty0 - 1 + r);
-        // upstream of the three neighbours; a border neighbour that is folded back counts twice
-        const float gl = Gs[c1 - 1] * (dup_l ? 2.f : 1.f), gm = Gs[c1], gr = Gs[c1 + 1] * (dup_r ? 2.f : 1.f);
+            for (int j = 0; j < 9; ++j) {
+                const float* pl = cs + j * T1::kCells + c1;
+                out[j] = pl[-1] * gl + pl[0] * gm + pl[1] * gr;
+            }
+        };
+        hsum(0, h[1]);
+        hsum(1, h[2]);
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            const float* pl = cs + j * T1::kCells + c1;
-            out[j] = pl[-1] * gl + pl[0] * gm + pl[1] * gr;
-        }
-    };
-    hsum(0, h[1]);
-    hsum(1, h[2]);
-#pragma unroll 1
-    for (int k = 0; k < kPixPerThread; ++k) {
+        for (int k = 0; k < kPixPerThread; ++k) {
 #pragma unroll
-        for (int j = 0; j < 9; ++j) { h[0][j] = h[1][j]; h[1][j] = h[2][j]; }
-        hsum(k + 2, h[2]);
-        const int gy = y0 + ty0 + k;
-        if (gx < W && gy < H) {
-            float V[9];
+            for (int j = 0; j < 9; ++j) { h[0][j] = h[1][j]; h[1][j] = h[2][j]; }
+            hsum(k + 2, h[2]);
+            const int gy = y0 + ty0 + k;
+            const bool own = gx < W && gy < H;
             const bool dup_u = (gy == 1), dup_d = (gy == H - 2);
+            float V[9];
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
                 float s = (h[0][j] + h[1][j]) + h[2][j];
@@ -349,23 +385,47 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
                 if (dup_d) s += h[2][j];
                 V[j] = s;
             }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                // d/dw of the SSIM terms around this pixel: V0 + 2 w V1 + t V2  (t = target)
+                const float t = own ? __ldg(c.tgt + ch * c.tgt_sc + gy * W + gx) : 0.f;
+                pq[k][2 * ch] = V[3 * ch] + t * V[3 * ch + 2];
+                pq[k][2 * ch + 1] = 2.0f * V[3 * ch + 1];
+            }
+        }
+        __syncthreads();                                    // every neighbour has read the coefficients
+#pragma unroll
+        for (int k = 0; k < kPixPerThread; ++k)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) cs[j * T1::kCells + T1::cell(tx, ty0 + k)] = pq[k][j];
+    }
+
+    // ---- phase D, one own pixel at a time: L1 / depth adjoints and the geometry adjoint ----
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < kPixPerThread; ++k) {
+        const int gy = y0 + ty0 + k;
+        if (gx < W && gy < H) {
             const int pix = gy * W + gx;
+            const int cell = T1::cell(tx, ty0 + k);
+            const float dep = __ldg(c.tdep + pix), m = __ldg(mask + pix);
+            const float d0 = depth_mask ? __ldg(coef + (int64_t)9 * n + pix) : 0.f;
             WarpPt p;
-            warp_point<F>(cam, A, gx, gy, __ldg(c.tdep + pix), p);
+            warp_point<F>(cam, A, gx, gy, dep, p);
             const TapIdx ti = make_taps(p, H, W);
-            const float m = __ldg(mask + pix);
-            const float Gd = Gs[T1::cell(tx, ty0 + k)];
-            float pd = 0.f, dd = 0.f;            Taps td;
+            const float Gd = Gs[cell];
+            // d loss / d dd = c_dep * mask - Gd * diff0   (diff = diff0 * (1 - dd), losses.py:176-177)
+            const float Gdd = sc.c_dep * m - Gd * d0;
+            float pd = 0.f, dd = 0.f;
+            Taps td;
             if (need_depth) {
                 td = load_taps(c.rdep, ti, W);
                 pd = blend(td, ti);
                 dd = depth_inconsistency(p.Z, pd);
             }
-            float G0 = Gd, Gdd = sc.c_dep * m;
-            if (depth_mask) {
-                G0 = Gd * (1.0f - dd);
-                Gdd -= Gd * __ldg(coef + (int64_t)9 * n + pix);
-            }
+            const float G0 = depth_mask ? Gd * (1.0f - dd) : Gd;
             float g_ix = 0.f, g_iy = 0.f;
             const float gl1 = G0 * A.third * L.w_l1;
 #pragma unroll
@@ -374,7 +434,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
                 const float w = blend(tv, ti);
                 const float t = __ldg(c.tgt + ch * c.tgt_sc + pix);
                 const float dlt = t - w;
-                float gwc = V[3 * ch] + 2.0f * w * V[3 * ch + 1] + t * V[3 * ch + 2];
+                float gwc = cs[(2 * ch) * T1::kCells + cell] + w * cs[(2 * ch + 1) * T1::kCells + cell];
                 if (fabsf(dlt) <= 1.0f) gwc += (dlt > 0.f) ? -gl1 : ((dlt < 0.f) ? gl1 : 0.f);
                 bilinear_grad(tv, p, gwc, g_ix, g_iy);
             }
