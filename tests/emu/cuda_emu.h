@@ -111,6 +111,8 @@ static inline unsigned atomicAdd(unsigned* addr, unsigned v) {
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 // IEEE single ops; build with -ffp-contract=off so plain * and + never fuse.
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -35,6 +35,17 @@ int check_launch(const char* what);
 
 constexpr int kWarp = 32;
 
+// Makes a per-thread base pointer opaque to the compiler so that it stays in registers:
+// without this ptxas re-derives `base + b * stride` (a 64-bit multiply-add chain from the
+// kernel parameters) at every use to save two registers.
+template <class T>
+__device__ __forceinline__ T* pin_pointer(T* p) {
+#ifndef TCSFM_HOST_EMU
+    asm volatile("" : "+l"(p));
+#endif
+    return p;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
     v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -42,6 +53,20 @@ __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
+}
+
+// One 4-byte cp.async global -> shared; `live == false` writes a zero instead of reading
+// `src` (the ignore-src form: a single LDGSTS with a predicate operand, where the
+// cuda_pipeline.h helper with a run-time zfill emits two predicated copies).
+__device__ __forceinline__ void async_copy4(float* smem_dst, const float* src, bool live) {
+#ifdef TCSFM_HOST_EMU
+    *smem_dst = live ? *src : 0.f;
+#else
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t"
+                 "cp.async.ca.shared.global [%0], [%1], 4, p;\n\t}"
+                 :: "r"(dst), "l"(src), "r"((unsigned)live) : "memory");
+#endif
 }
 
 // Block-wide sum of N per-thread partials -> one atomicAdd per value per block.

@@ -35,9 +35,6 @@ namespace tcsfm {
 #define TCSFM_BWD_MIN_BLOCKS 4      // measured: 4 CTAs/SM with ~200 B of spills beats 2-3 CTAs/SM without (latency bound)
 #endif
 
-#ifndef TCSFM_BWD_MIN2
-#define TCSFM_BWD_MIN2 1
-#endif
 #ifndef TCSFM_BWD_STAGE_UNROLL
 #define TCSFM_BWD_STAGE_UNROLL 1
 #endif
@@ -54,17 +51,17 @@ struct PairLaunch {
 
 struct PairCtx {
     const float* tgt; const float* ref; const float* tdep; const float* rdep;
-    int64_t tgt_sc, ref_sc;
+    int tgt_sc, ref_sc;              // channel strides; fill_launch checks that 3 planes stay below 2^31 elements
 };
 
 __device__ __forceinline__ PairCtx make_ctx(const tcsfm_pair_group& g, int b, int n) {
     PairCtx c;
-    c.tgt = g.tgt_img + b * g.tgt_sb;
-    c.ref = g.ref_img + b * g.ref_sb;
-    c.tdep = g.tgt_depth + (int64_t)b * n;
-    c.rdep = g.ref_depth ? g.ref_depth + (int64_t)b * n : nullptr;
-    c.tgt_sc = g.tgt_sc;
-    c.ref_sc = g.ref_sc;
+    c.tgt = pin_pointer(g.tgt_img + b * g.tgt_sb);
+    c.ref = pin_pointer(g.ref_img + b * g.ref_sb);
+    c.tdep = pin_pointer(g.tgt_depth + (int64_t)b * n);
+    c.rdep = pin_pointer(g.ref_depth ? g.ref_depth + (int64_t)b * n : nullptr);
+    c.tgt_sc = (int)g.tgt_sc;
+    c.ref_sc = (int)g.ref_sc;
     return c;
 }
 
@@ -181,7 +178,7 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
 
     // ---- phase C: 3x3 statistics down the strip, one channel at a time ----
     float esum[kPixPerThread];
-    float* coef_base = g.coef ? g.coef + (int64_t)b * kCoefPlanes * n : nullptr;
+    float* coef_base = pin_pointer(g.coef ? g.coef + (int64_t)b * kCoefPlanes * n : nullptr);   // offsets below: < 2^31 (fill_launch)
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const float2* plane = tw + ch * T1::kCells;
@@ -215,8 +212,8 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
                 // d diff / d ssim_c = (1 - dd) * (1/3) * w_ssim ; the backward multiplies by its upstream
                 const float gq = (depth_mask ? (1.0f - own_dd[k]) : 1.0f) * A.third * L.w_ssim;
                 const SsimCoef kf = ssim_coef(s, t, gq);            // x = target, y = warped
-                float* cp = coef_base + (int64_t)(3 * ch) * n + gy * W + gx;
-                cp[0] = kf.Ay; cp[n] = kf.B; cp[2 * (int64_t)n] = kf.Cc;
+                const int o = (3 * ch) * n + gy * W + gx;
+                coef_base[o] = kf.Ay; coef_base[o + n] = kf.B; coef_base[o + 2 * n] = kf.Cc;
             }
         }
     }
@@ -232,7 +229,7 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
             const int64_t o = (int64_t)b * n + gy * W + gx;
             if (g.diff_img) g.diff_img[o] = diff;
             if (g.mask) g.mask[o] = own_mask[k];
-            if (coef_base) coef_base[(int64_t)9 * n + gy * W + gx] = diff0;
+            if (coef_base) coef_base[9 * n + gy * W + gx] = diff0;
             part[0] += diff * own_mask[k];
             part[1] += own_mask[k];
             if (depth_consist) part[2] += own_dd[k] * own_mask[k];
@@ -244,12 +241,18 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
 // ---------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------
-struct BwdScalars { float c_rep, c_dep, g_min; };
+struct BwdScalars {
+    float c_rep, c_dep, g_min;
+    const float* min_self;          // this group's plane of the min-reprojection candidates (batch element b)
+    const float* min_other;         // the other candidate's plane when there are exactly two
+};
 
-__device__ __forceinline__ BwdScalars bwd_scalars(const tcsfm_pair_group& g, bool depth_consist) {
+__device__ __forceinline__ BwdScalars bwd_scalars(const tcsfm_pair_group& g, bool depth_consist, int64_t bn) {
     BwdScalars s;
     s.c_rep = 0.f; s.c_dep = 0.f;
     s.g_min = g.min_base ? __ldg(g.g_min) : 0.f;
+    s.min_self = pin_pointer(g.min_base ? g.min_base + bn + (int64_t)g.min_index * g.min_stride : nullptr);
+    s.min_other = pin_pointer((g.min_base && g.min_count == 2) ? g.min_base + bn + (int64_t)(1 - g.min_index) * g.min_stride : nullptr);
     if (g.g_scalars) {
         const float s1 = __ldg(g.sums + 1);
         if (s1 > 10000.0f) {                        // mean_on_mask, losses.py:144
@@ -263,18 +266,18 @@ __device__ __forceinline__ BwdScalars bwd_scalars(const tcsfm_pair_group& g, boo
 // Upstream gradient of diff_img at pixel `pix` of batch element b: the explicit per-pixel
 // gradient, the masked-mean term and the per-pixel min routing (losses.py:129-132).
 __device__ __forceinline__ float upstream_diff(const tcsfm_pair_group& g, const BwdScalars& sc, const float* gdiff,
-                                               const float* mask, int64_t bn, int pix, float m) {
+                                               int64_t bn, int pix, float m) {
     float Gd = sc.c_rep * m;
     if (gdiff) Gd += __ldg(gdiff + pix);
-    if (g.min_base) {
-        const float* mine = g.min_base + bn + pix;
-        const float v = __ldg(mine + (int64_t)g.min_index * g.min_stride);
+    if (sc.min_self) {
+        const float v = __ldg(sc.min_self + pix);
         bool win = true;
         // torch.min(dim): the first index holding the minimum wins; a NaN is the minimum
-        if (TCSFM_BWD_MIN2 && g.min_count == 2) {                     // the usual two sources: branch-free, both loads in flight
-            const float o = __ldg(mine + (int64_t)(1 - g.min_index) * g.min_stride);
+        if (sc.min_other) {                          // the usual two sources: branch-free, both loads in flight
+            const float o = __ldg(sc.min_other + pix);
             win = (g.min_index == 1) ? !(o <= v || o != o) : !(o < v || (o != o && v == v));
         } else {
+            const float* mine = g.min_base + bn + pix;
             for (int j = 0; j < g.min_count; ++j) {
                 if (j == g.min_index) continue;
                 const float o = __ldg(mine + (int64_t)j * g.min_stride);
@@ -307,10 +310,10 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     const bool depth_consist = (L.flags & TCSFM_DEPTH_CONSIST) != 0;
     const bool need_depth = depth_mask || depth_consist;
     const bool shared_grads = (L.flags & TCSFM_SHARED_GRADS) != 0;
-    const BwdScalars sc = bwd_scalars(g, depth_consist);
-    const float* gdiff = g.g_diff ? g.g_diff + (int64_t)b * n : nullptr;
-    const float* mask = g.mask + (int64_t)b * n;
-    const float* coef = g.coef + (int64_t)b * kCoefPlanes * n;
+    const BwdScalars sc = bwd_scalars(g, depth_consist, (int64_t)b * n);
+    const float* gdiff = pin_pointer(g.g_diff ? g.g_diff + (int64_t)b * n : nullptr);
+    const float* mask = pin_pointer(g.mask + (int64_t)b * n);
+    const float* coef = pin_pointer(g.coef + (int64_t)b * kCoefPlanes * n);      // offsets below: < 2^31 (fill_launch)
     const int tx = threadIdx.x & (kTileW - 1);
     const int ty0 = (threadIdx.x >> 6) * kPixPerThread;
     const int gx = x0 + tx;
@@ -336,11 +339,11 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         // coefficients only matter where the upstream gradient is non-zero (masked-out pixels of
         // the inverse groups, the losing source of the per-pixel min): skip their 36 B/px
         const float m = inside ? __ldg(mask + pix) : 0.f;
-        const float Gd = inside ? upstream_diff(g, sc, gdiff, mask, (int64_t)b * n, pix, m) : 0.f;
+        const float Gd = inside ? upstream_diff(g, sc, gdiff, (int64_t)b * n, pix, m) : 0.f;
         const bool live = Gd != 0.f;
 #pragma unroll
         for (int j = 0; j < 9; ++j)
-            __pipeline_memcpy_async(cs + j * T1::kCells + cell, coef + (int64_t)j * n + pix, 4, live ? 0 : 4);
+            async_copy4(cs + j * T1::kCells + cell, coef + (j * n + pix), live);
         Gs[cell] = Gd;
     }
     __pipeline_commit();
@@ -411,7 +414,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             const int pix = gy * W + gx;
             const int cell = T1::cell(tx, ty0 + k);
             const float dep = __ldg(c.tdep + pix), m = __ldg(mask + pix);
-            const float d0 = depth_mask ? __ldg(coef + (int64_t)9 * n + pix) : 0.f;
+            const float d0 = depth_mask ? __ldg(coef + (9 * n + pix)) : 0.f;
             WarpPt p;
             warp_point<F>(cam, A, gx, gy, dep, p);
             const TapIdx ti = make_taps(p, H, W);
@@ -442,13 +445,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             if (need_depth && Gdd != 0.f) {
                 depth_inconsistency_adjoint(p.Z, pd, Gdd, g_Z, g_pd);
                 bilinear_grad(td, p, g_pd, g_ix, g_iy);
-                if (g.g_ref_depth && g_pd != 0.f) {
-                    float* r0 = g.g_ref_depth + (int64_t)b * n + ti.off;
-                    if (ti.nw) atomicAdd(r0, g_pd * ti.w_nw);
-                    if (ti.ne) atomicAdd(r0 + 1, g_pd * ti.w_ne);
-                    if (ti.sw) atomicAdd(r0 + W, g_pd * ti.w_sw);
-                    if (ti.se) atomicAdd(r0 + W + 1, g_pd * ti.w_se);
-                }
+                if (g.g_ref_depth && g_pd != 0.f) scatter_taps(g.g_ref_depth + (int64_t)b * n, ti, g_pd, W);
             }
             const GeomGrad gg = geom_adjoint(cam, A, p, g_ix, g_iy, g_Z);
             if (g.g_tgt_depth) {
@@ -478,6 +475,11 @@ static int fill_launch(PairLaunch& L, const tcsfm_pair_group* groups, int n, int
         const tcsfm_pair_group& g = groups[i];
         if (!g.tgt_img || !g.ref_img || !g.tgt_depth || !g.kinv || !g.proj || !g.sums) {
             set_error("%s: group %d has a null input pointer", who, i); return 1;
+        }
+        // in-kernel offsets inside one batch element are 32-bit
+        const int64_t lim = ((int64_t)1 << 31) - 1 - (int64_t)H * W;
+        if (g.tgt_sc < 0 || g.ref_sc < 0 || 2 * g.tgt_sc > lim || 2 * g.ref_sc > lim) {
+            set_error("%s: group %d: channel stride out of range", who, i); return 1;
         }
         if (need_depth && !g.ref_depth) { set_error("%s: group %d needs ref_depth for the depth terms", who, i); return 1; }
         if (bwd && (!g.mask || !g.coef)) { set_error("%s: group %d: backward needs the forward's mask and coef workspace", who, i); return 1; }

@@ -46,14 +46,6 @@ warp_fwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
     if (out_cd) out_cd[o] = p.Z;
 }
 
-__device__ __forceinline__ void scatter_taps(float* __restrict__ plane, const TapIdx& t, float g, int W) {
-    float* r0 = plane + t.off;
-    if (t.nw) atomicAdd(r0, g * t.w_nw);
-    if (t.ne) atomicAdd(r0 + 1, g * t.w_ne);
-    if (t.sw) atomicAdd(r0 + W, g * t.w_sw);
-    if (t.se) atomicAdd(r0 + W + 1, g * t.w_se);
-}
-
 template <int F>
 __global__ void __launch_bounds__(kWarpThreads, 3)
 warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
