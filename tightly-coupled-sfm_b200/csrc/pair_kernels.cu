@@ -35,9 +35,6 @@ namespace tcsfm {
 #define TCSFM_BWD_MIN_BLOCKS 4      // measured: 4 CTAs/SM with ~200 B of spills beats 2-3 CTAs/SM without (latency bound)
 #endif
 
-#ifndef TCSFM_BWD_STAGE_UNROLL
-#define TCSFM_BWD_STAGE_UNROLL 1
-#endif
 
 constexpr int kMaxGroups = 8;
 constexpr int kCoefPlanes = 10;      // 3 channels x (A, B, C) + the un-weighted photometric error
@@ -323,23 +320,45 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     //      image), next to the upstream gradient of diff_img at each ring pixel ----
     float* Gs = cs + 9 * T1::kCells;               // [cells] upstream gradient (0 outside the image)
     constexpr int kStageIters = (T1::kCells + kTileThreads - 1) / kTileThreads;
-#if TCSFM_BWD_STAGE_UNROLL
+    // pass 1: request everything the upstream gradient of this thread's cells depends on (branch
+    // free, so that the loads of all cells are in flight together); pass 2: combine and copy
+    int st_pix[kStageIters];
+    float st_m[kStageIters], st_g[kStageIters], st_v[kStageIters], st_o[kStageIters];
+    const bool two_way = sc.min_other != nullptr;                    // per-pixel min over exactly two sources
 #pragma unroll
-#else
-#pragma unroll 1
-#endif
+    for (int it = 0; it < kStageIters; ++it) {
+        const int cell = threadIdx.x + it * kTileThreads;
+        int cx, cy;
+        T1::cell_xy(cell < T1::kCells ? cell : 0, cx, cy);
+        const int qx = x0 + cx, qy = y0 + cy;
+        const bool inside = cell < T1::kCells && qx >= 0 && qx < W && qy >= 0 && qy < H;
+        const int pix = inside ? qy * W + qx : 0;                    // pixel 0 stands in: always a valid address
+        st_pix[it] = inside ? pix : -1;
+        st_m[it] = __ldg(mask + pix);
+        st_g[it] = gdiff ? __ldg(gdiff + pix) : 0.f;
+        st_v[it] = two_way ? __ldg(sc.min_self + pix) : 0.f;
+        st_o[it] = two_way ? __ldg(sc.min_other + pix) : 0.f;
+    }
+#pragma unroll
     for (int it = 0; it < kStageIters; ++it) {
         const int cell = threadIdx.x + it * kTileThreads;
         if (cell >= T1::kCells) break;
-        int cx, cy;
-        T1::cell_xy(cell, cx, cy);
-        const int qx = x0 + cx, qy = y0 + cy;
-        const bool inside = qx >= 0 && qx < W && qy >= 0 && qy < H;
-        const int pix = inside ? qy * W + qx : 0;
+        const bool inside = st_pix[it] >= 0;
+        const int pix = inside ? st_pix[it] : 0;
+        float Gd = 0.f;
+        if (inside) {
+            if (two_way || !sc.min_self) {
+                Gd = sc.c_rep * st_m[it] + st_g[it];
+                // torch.min(dim): the first index holding the minimum wins; a NaN is the minimum
+                const float v = st_v[it], o = st_o[it];
+                const bool win = (g.min_index == 1) ? !(o <= v || o != o) : !(o < v || (o != o && v == v));
+                if (two_way && win) Gd += sc.g_min;
+            } else {
+                Gd = upstream_diff(g, sc, gdiff, (int64_t)b * n, pix, st_m[it]);
+            }
+        }
         // coefficients only matter where the upstream gradient is non-zero (masked-out pixels of
         // the inverse groups, the losing source of the per-pixel min): skip their 36 B/px
-        const float m = inside ? __ldg(mask + pix) : 0.f;
-        const float Gd = inside ? upstream_diff(g, sc, gdiff, (int64_t)b * n, pix, m) : 0.f;
         const bool live = Gd != 0.f;
 #pragma unroll
         for (int j = 0; j < 9; ++j)
