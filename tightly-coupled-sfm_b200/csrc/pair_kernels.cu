@@ -375,6 +375,12 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     //      neighbour twice.  Per channel the result is the gradient wrt the warped value as a
     //      line in that value, g_w = P + w * Q; (P, Q) replace the coefficients of the own cells
     //      in shared memory so that phase D starts with an empty register file. ----
+    float dep_own[kPixPerThread];                  // heads phase D's longest chain: requested before phase C
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+        const int gy = y0 + ty0 + k;
+        dep_own[k] = (gx < W && gy < H) ? __ldg(c.tdep + gy * W + gx) : 1.0f;
+    }
     {
         float pq[kPixPerThread][6];
         float h[3][9];
@@ -420,6 +426,8 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         for (int k = 0; k < kPixPerThread; ++k)
 #pragma unroll
             for (int j = 0; j < 6; ++j) cs[j * T1::kCells + T1::cell(tx, ty0 + k)] = pq[k][j];
+#pragma unroll
+        for (int k = 0; k < kPixPerThread; ++k) cs[6 * T1::kCells + T1::cell(tx, ty0 + k)] = dep_own[k];
     }
 
     // ---- phase D, one own pixel at a time: L1 / depth adjoints and the geometry adjoint ----
@@ -432,7 +440,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         if (gx < W && gy < H) {
             const int pix = gy * W + gx;
             const int cell = T1::cell(tx, ty0 + k);
-            const float dep = __ldg(c.tdep + pix), m = __ldg(mask + pix);
+            const float dep = cs[6 * T1::kCells + cell], m = __ldg(mask + pix);
             const float d0 = depth_mask ? __ldg(coef + (9 * n + pix)) : 0.f;
             WarpPt p;
             warp_point<F>(cam, A, gx, gy, dep, p);
