@@ -55,6 +55,16 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Store through a pinned pointer: the asm above hides the address space from the compiler,
+// which would otherwise emit a generic ST instead of STG.
+__device__ __forceinline__ void store_global(float* p, float v) {
+#ifdef TCSFM_HOST_EMU
+    *p = v;
+#else
+    asm volatile("st.global.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+#endif
+}
+
 // One 4-byte cp.async global -> shared; `live == false` writes a zero instead of reading
 // `src` (the ignore-src form: a single LDGSTS with a predicate operand, where the
 // cuda_pipeline.h helper with a run-time zfill emits two predicated copies).

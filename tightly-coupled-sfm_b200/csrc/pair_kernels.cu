@@ -62,18 +62,23 @@ __device__ __forceinline__ PairCtx make_ctx(const tcsfm_pair_group& g, int b, in
     return c;
 }
 
-// Fills one shared-memory cell with (target, warped source) of the image pixel (rx, ry).
+// Fills one shared-memory cell with (target, warped source) of the image pixel (rx, ry);
+// returns the validity of the warp and, when asked, the depth inconsistency at that pixel.
 template <int F>
 __device__ __forceinline__ void fill_cell(const PairCtx& c, const Cam& cam, const Arith& A, int rx, int ry,
-                                          float depth, float2* tw, int cells, int cell, WarpPt& p, TapIdx& ti) {
+                                          float depth, float2* tw, int cells, int cell, bool want_dd,
+                                          bool& valid, float& dd) {
     const int pix = ry * A.W + rx;
+    WarpPt p;
     warp_point<F>(cam, A, rx, ry, depth, p);
-    ti = make_taps(p, A.H, A.W);
+    const TapIdx ti = make_taps(p, A.H, A.W);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        const float w = blend(load_taps(c.ref + ch * c.ref_sc, ti, A.W), ti);
-        tw[ch * cells + cell] = make_float2(__ldg(c.tgt + ch * c.tgt_sc + pix), w);
+        const float w = blend(load_taps(c.ref, ch * c.ref_sc, ti, A.W), ti);
+        tw[ch * cells + cell] = make_float2(__ldg(c.tgt + (ch * c.tgt_sc + pix)), w);
     }
+    valid = p.valid;
+    dd = want_dd ? depth_inconsistency(p.Z, blend(load_taps(c.rdep, 0, ti, A.W), ti)) : 0.f;
 }
 
 __device__ __forceinline__ void zero_cell(float2* tw, int cells, int cell) {
@@ -138,13 +143,12 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
         const int gy = y0 + ty0 + k;
         const int cell = T1::cell(tx, ty0 + k);
         float m = 0.f, dd = 0.f;
-        WarpPt p;
-        TapIdx ti;
+        bool valid = false;
         const bool own = gx < W && gy < H;
-        if (src_ok[k]) fill_cell<F>(c, cam, A, src_x[k], src_y[k], src_depth[k], tw, T1::kCells, cell, p, ti);
+        if (src_ok[k]) fill_cell<F>(c, cam, A, src_x[k], src_y[k], src_depth[k], tw, T1::kCells, cell, need_depth && own, valid, dd);
         else zero_cell(tw, T1::kCells, cell);
         if (own) {
-            m = p.valid ? 1.f : 0.f;
+            m = valid ? 1.f : 0.f;
             if (auto_mask) {
                 const int pix = gy * W + gx;
                 float l1[3], ar[3];
@@ -152,11 +156,10 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
                 for (int ch = 0; ch < 3; ++ch) {
                     const float2 v = tw[ch * T1::kCells + cell];
                     l1[ch] = clamp01_nan(fabsf(__fsub_rn(v.x, v.y)));
-                    ar[ch] = fabsf(__fsub_rn(v.x, __ldg(c.ref + ch * c.ref_sc + pix)));
+                    ar[ch] = fabsf(__fsub_rn(v.x, __ldg(c.ref + (ch * c.ref_sc + pix))));
                 }
                 if (!(mean3<F>(l1[0], l1[1], l1[2], A) < mean3<F>(ar[0], ar[1], ar[2], A))) m = 0.f;
             }
-            if (need_depth) dd = depth_inconsistency(p.Z, blend(load_taps(c.rdep, ti, W), ti));
         }
         own_mask[k] = m;
         own_dd[k] = dd;
@@ -166,9 +169,9 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
         int cx, cy;
         ring_cell(threadIdx.x, cx, cy);
         const int cell = T1::cell(cx, cy);
-        WarpPt p;
-        TapIdx ti;
-        if (src_ok[kPixPerThread]) fill_cell<F>(c, cam, A, src_x[kPixPerThread], src_y[kPixPerThread], src_depth[kPixPerThread], tw, T1::kCells, cell, p, ti);
+        bool valid;
+        float dd;
+        if (src_ok[kPixPerThread]) fill_cell<F>(c, cam, A, src_x[kPixPerThread], src_y[kPixPerThread], src_depth[kPixPerThread], tw, T1::kCells, cell, false, valid, dd);
         else zero_cell(tw, T1::kCells, cell);
     }
     __syncthreads();
@@ -210,7 +213,9 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
                 const float gq = (depth_mask ? (1.0f - own_dd[k]) : 1.0f) * A.third * L.w_ssim;
                 const SsimCoef kf = ssim_coef(s, t, gq);            // x = target, y = warped
                 const int o = (3 * ch) * n + gy * W + gx;
-                coef_base[o] = kf.Ay; coef_base[o + n] = kf.B; coef_base[o + 2 * n] = kf.Cc;
+                store_global(coef_base + o, kf.Ay);
+                store_global(coef_base + (o + n), kf.B);
+                store_global(coef_base + (o + 2 * n), kf.Cc);
             }
         }
     }
@@ -226,7 +231,7 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
             const int64_t o = (int64_t)b * n + gy * W + gx;
             if (g.diff_img) g.diff_img[o] = diff;
             if (g.mask) g.mask[o] = own_mask[k];
-            if (coef_base) coef_base[9 * n + gy * W + gx] = diff0;
+            if (coef_base) store_global(coef_base + (9 * n + gy * W + gx), diff0);
             part[0] += diff * own_mask[k];
             part[1] += own_mask[k];
             if (depth_consist) part[2] += own_dd[k] * own_mask[k];
@@ -416,7 +421,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 // d/dw of the SSIM terms around this pixel: V0 + 2 w V1 + t V2  (t = target)
-                const float t = own ? __ldg(c.tgt + ch * c.tgt_sc + gy * W + gx) : 0.f;
+                const float t = own ? __ldg(c.tgt + (ch * c.tgt_sc + gy * W + gx)) : 0.f;
                 pq[k][2 * ch] = V[3 * ch] + t * V[3 * ch + 2];
                 pq[k][2 * ch + 1] = 2.0f * V[3 * ch + 1];
             }
@@ -451,7 +456,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             float pd = 0.f, dd = 0.f;
             Taps td;
             if (need_depth) {
-                td = load_taps(c.rdep, ti, W);
+                td = load_taps(c.rdep, 0, ti, W);
                 pd = blend(td, ti);
                 dd = depth_inconsistency(p.Z, pd);
             }
@@ -460,9 +465,9 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             const float gl1 = G0 * A.third * L.w_l1;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const Taps tv = load_taps(c.ref + ch * c.ref_sc, ti, W);
+                const Taps tv = load_taps(c.ref, ch * c.ref_sc, ti, W);
                 const float w = blend(tv, ti);
-                const float t = __ldg(c.tgt + ch * c.tgt_sc + pix);
+                const float t = __ldg(c.tgt + (ch * c.tgt_sc + pix));
                 const float dlt = t - w;
                 float gwc = cs[(2 * ch) * T1::kCells + cell] + w * cs[(2 * ch + 1) * T1::kCells + cell];
                 if (fabsf(dlt) <= 1.0f) gwc += (dlt > 0.f) ? -gl1 : ((dlt < 0.f) ? gl1 : 0.f);
@@ -472,7 +477,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             if (need_depth && Gdd != 0.f) {
                 depth_inconsistency_adjoint(p.Z, pd, Gdd, g_Z, g_pd);
                 bilinear_grad(td, p, g_pd, g_ix, g_iy);
-                if (g.g_ref_depth && g_pd != 0.f) scatter_taps(g.g_ref_depth + (int64_t)b * n, ti, g_pd, W);
+                if (g.g_ref_depth && g_pd != 0.f) scatter_taps(g.g_ref_depth + (int64_t)b * n, 0, ti, g_pd, W);
             }
             const GeomGrad gg = geom_adjoint(cam, A, p, g_ix, g_iy, g_Z);
             if (g.g_tgt_depth) {

@@ -33,7 +33,7 @@ warp_fwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
     if (out_img || out_stack) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-            const float w = blend(load_taps(img + b * img_sb + ch * img_sc, ti, A.W), ti);
+            const float w = blend(load_taps(img + b * img_sb + ch * img_sc, 0, ti, A.W), ti);
             if (out_img) out_img[((int64_t)b * 3 + ch) * n + pix] = w;
             if (out_stack) {          // next pose-net input: [target * valid | reconstruction], train_mono.py:74-76
                 out_stack[((int64_t)b * 6 + 3 + ch) * n + pix] = w;
@@ -42,7 +42,7 @@ warp_fwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
         }
     }
     if (out_valid) out_valid[o] = p.valid ? 1.f : 0.f;
-    if (out_pd) out_pd[o] = blend(load_taps(ref_depth + (int64_t)b * n, ti, A.W), ti);
+    if (out_pd) out_pd[o] = blend(load_taps(ref_depth + (int64_t)b * n, 0, ti, A.W), ti);
     if (out_cd) out_cd[o] = p.Z;
 }
 
@@ -78,16 +78,16 @@ warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int64_t img_sc,
             for (int ch = 0; ch < 3; ++ch) {
                 float g = g_oimg ? __ldg(g_oimg + ((int64_t)b * 3 + ch) * n + pix) : 0.f;
                 if (g_ostack) g += __ldg(g_ostack + ((int64_t)b * 6 + 3 + ch) * n + pix);
-                const Taps t = load_taps(img + b * img_sb + ch * img_sc, ti, A.W);
+                const Taps t = load_taps(img + b * img_sb + ch * img_sc, 0, ti, A.W);
                 bilinear_grad(t, p, g, g_ix, g_iy);
-                if (g_img) scatter_taps(g_img + ((int64_t)b * 3 + ch) * n, ti, g, A.W);
+                if (g_img) scatter_taps(g_img + ((int64_t)b * 3 + ch) * n, 0, ti, g, A.W);
             }
         }
         if (g_opd) {
             const float g = __ldg(g_opd + o);
-            const Taps t = load_taps(ref_depth + (int64_t)b * n, ti, A.W);
+            const Taps t = load_taps(ref_depth + (int64_t)b * n, 0, ti, A.W);
             bilinear_grad(t, p, g, g_ix, g_iy);
-            if (g_ref_depth) scatter_taps(g_ref_depth + (int64_t)b * n, ti, g, A.W);
+            if (g_ref_depth) scatter_taps(g_ref_depth + (int64_t)b * n, 0, ti, g, A.W);
         }
         const float g_Z = g_ocd ? __ldg(g_ocd + o) : 0.f;
         const GeomGrad gg = geom_adjoint(c, A, p, g_ix, g_iy, g_Z);
