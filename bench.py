@@ -100,7 +100,7 @@ def run_step(loss_mod, inp, n_src, need_value=False):
         t.grad = None
     out = loss_mod([inp["source%d" % j] for j in range(n_src)], inp["target"], [poses, poses_inv],
                    [[d] + ex for d, ex in zip(disps, extra)], inp["K"])
-    total = out["total"].sum()
+    total = out["total"]            # [1]; backward() on it directly, like train_mono.py:193
     total.backward()
     return total
 
@@ -486,7 +486,7 @@ def main():
         e2e = {"in": [graphs[0], graphs[1]], "bufs": [sets[0], sets[1]],
                "h2d_done": [torch.cuda.Event(), torch.cuda.Event()],
                "compute_done": [torch.cuda.Event(), torch.cuda.Event()],
-               "loss_host": [torch.zeros((), pin_memory=True), torch.zeros((), pin_memory=True)]}
+               "loss_host": [torch.zeros(1, pin_memory=True), torch.zeros(1, pin_memory=True)]}
         for ev in e2e["compute_done"]:
             ev.record()
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 5
+#define TCSFM_ABI_VERSION 6
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -192,10 +192,15 @@ typedef struct tcsfm_frame_cfg {
 } tcsfm_frame_cfg;
 
 /* out[3] = (l_reconstruct_inverse, l_reconstruct_forward, l_depth) of one scale, from the pair
- * kernels' sums [G,4] and the min-reduce sum (mean_on_mask's 10000-pixel rule on the device). */
-int tcsfm_frame_finalize(const float* sums, const float* min_sum, const tcsfm_frame_cfg* cfg, float* out, void* stream);
-/* g_out[3] -> g_scalars [G,2] and g_min [1], the upstream scalars tcsfm_pair_loss_bwd consumes. */
-int tcsfm_frame_bwd_prepare(const float* g_out, const tcsfm_frame_cfg* cfg, float* g_scalars, float* g_min, void* stream);
+ * kernels' sums [G,4] and the min-reduce sum (mean_on_mask's 10000-pixel rule on the device).
+ * total[1] (may be NULL) = (out[0] + out[1]) + out[2], the order Compute_Loss.forward adds the
+ * terms into losses['total'] (losses.py:134-138). */
+int tcsfm_frame_finalize(const float* sums, const float* min_sum, const tcsfm_frame_cfg* cfg, float* out, float* total,
+                         void* stream);
+/* Upstream gradients of the three terms (g_out[3], may be NULL) and of their sum (g_total[1],
+ * may be NULL) -> g_scalars [G,2] and g_min [1], the upstream scalars tcsfm_pair_loss_bwd consumes. */
+int tcsfm_frame_bwd_prepare(const float* g_out, const float* g_total, const tcsfm_frame_cfg* cfg, float* g_scalars,
+                            float* g_min, void* stream);
 
 #ifdef __cplusplus
 }

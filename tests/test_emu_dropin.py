@@ -122,6 +122,38 @@ def test_compute_loss_forward_backward(emu_ops, case, tag):
             assert rel_l2(got, ref_g) < 1e-3, (name, j)
 
 
+def test_compute_loss_mixed_upstream(emu_ops):
+    """Gradients through the individual terms and through `total` together (both upstream
+    pointers of tcsfm_frame_bwd_prepare), and an in-place add on `total` like
+    train_mono.py:181, against the oracle."""
+    from oracle import ref_torch as O
+    g = Golden(goldens.CASES[0])
+    fr = g.frames()
+    cfg = goldens.LOSS_CFGS["full"]
+    grads = []
+    for impl in ("ours", "oracle"):
+        disps = [leaf(d) for d in fr["disps"]]
+        poses, poses_inv = [leaf(p) for p in fr["poses"]], [leaf(p) for p in fr["poses_inv"]]
+        args = (fr["sources"], fr["target"], [poses, poses_inv], [[disps[0]], [disps[1]], [disps[2]]], fr["K"])
+        out = losses.Compute_Loss(cfg)(*args) if impl == "ours" else O.compute_loss(cfg, *args)
+        extra = 0.01 * (poses[0] ** 2).sum().reshape(1)
+        out["total"] += extra                                   # in place, as the trainer adds l_pose_consist
+        (2.0 * out["total"] + 3.0 * out["l_depth"] - 0.5 * out["l_reconstruct_forward"]).sum().backward()
+        grads.append([torch.zeros_like(t) if t.grad is None else t.grad.clone() for t in disps + poses + poses_inv])
+    for a, b in zip(*grads):
+        assert rel_l2(a, b) < 1e-3
+
+
+def test_compute_loss_unused_terms_need_no_backward(emu_ops):
+    g = Golden(goldens.CASES[0])
+    fr = g.frames()
+    disps = [leaf(d) for d in fr["disps"]]
+    out = losses.Compute_Loss(goldens.LOSS_CFGS["full"])(
+        fr["sources"], fr["target"], [fr["poses"], fr["poses_inv"]], [[disps[0]], [disps[1]], [disps[2]]], fr["K"])
+    out["l_depth"].sum().backward()                             # only the [3] upstream, total's is absent
+    assert all(d.grad is not None and torch.isfinite(d.grad).all() for d in disps)
+
+
 @pytest.mark.parametrize("case", goldens.CASES)
 def test_pft_path(emu_ops, case):
     """solve_pose_iteratively(return_errors=True) + compute_optimization_loss against

@@ -239,20 +239,25 @@ def make_frame_cfg(roles, w_inverse, w_depth, n_min_pixels):
 
 
 def frame_finalize(lib, sums, min_sum, cfg):
+    """-> terms [3] = (l_reconstruct_inverse, l_reconstruct_forward, l_depth), total [1] = their sum."""
     out = torch.empty((3,), dtype=torch.float32, device=sums.device)
+    total = torch.empty((1,), dtype=torch.float32, device=sums.device)
     with _timing.launch("frame_finalize", sums.is_cuda):
-        rc = lib.tcsfm_frame_finalize(_ptr(sums), _ptr(min_sum), C.byref(cfg), _ptr(out), _stream(sums))
+        rc = lib.tcsfm_frame_finalize(_ptr(sums), _ptr(min_sum), C.byref(cfg), _ptr(out), _ptr(total), _stream(sums))
     _cabi.check(lib, rc)
     _timing.count_launch()
-    return out
+    return out, total
 
 
-def frame_bwd_prepare(lib, g_out, cfg):
-    g_out = _f32c(g_out, "g_out")
-    g_scalars = torch.empty((cfg.n_groups, 2), dtype=torch.float32, device=g_out.device)
-    g_min = torch.empty((1,), dtype=torch.float32, device=g_out.device)
-    with _timing.launch("frame_bwd_prepare", g_out.is_cuda):
-        rc = lib.tcsfm_frame_bwd_prepare(_ptr(g_out), C.byref(cfg), _ptr(g_scalars), _ptr(g_min), _stream(g_out))
+def frame_bwd_prepare(lib, g_terms, g_total, cfg):
+    """Upstream of the three terms ([3] or None) and of their sum ([1] or None)."""
+    ref = g_terms if g_terms is not None else g_total
+    g_terms = None if g_terms is None else _f32c(g_terms, "g_terms")
+    g_total = None if g_total is None else _f32c(g_total, "g_total")
+    g_scalars = torch.empty((cfg.n_groups, 2), dtype=torch.float32, device=ref.device)
+    g_min = torch.empty((1,), dtype=torch.float32, device=ref.device)
+    with _timing.launch("frame_bwd_prepare", ref.is_cuda):
+        rc = lib.tcsfm_frame_bwd_prepare(_ptr(g_terms), _ptr(g_total), C.byref(cfg), _ptr(g_scalars), _ptr(g_min), _stream(ref))
     _cabi.check(lib, rc)
     _timing.count_launch()
     return g_scalars, g_min

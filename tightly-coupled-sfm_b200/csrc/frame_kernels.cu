@@ -165,7 +165,7 @@ min_reduce_kernel(const float* __restrict__ base, int64_t stride, int count, int
 }
 
 __global__ void frame_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ min_sum, tcsfm_frame_cfg cfg,
-                                      float* __restrict__ out) {
+                                      float* __restrict__ out, float* __restrict__ total) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float l_inv = 0.f, l_dep = 0.f;
     for (int g = 0; g < cfg.n_groups; ++g) {
@@ -176,19 +176,23 @@ __global__ void frame_finalize_kernel(const float* __restrict__ sums, const floa
         if (cfg.w_depth != 0.f) l_dep = __fadd_rn(l_dep, __fmul_rn(cfg.w_depth, l_d));          // :114-115,:121-122
         if (cfg.role[g] == 0) l_inv = __fadd_rn(l_inv, __fmul_rn(cfg.w_inverse, l_rep));        // :116
     }
+    const float l_fwd = min_sum ? __fdiv_rn(min_sum[0], (float)cfg.n_min_pixels) : 0.f;         // :129-132
     out[0] = l_inv;
-    out[1] = min_sum ? __fdiv_rn(min_sum[0], (float)cfg.n_min_pixels) : 0.f;                    // :129-132
+    out[1] = l_fwd;
     out[2] = l_dep;
+    if (total) total[0] = __fadd_rn(__fadd_rn(l_inv, l_fwd), l_dep);                            // :134-138
 }
 
-__global__ void frame_bwd_prepare_kernel(const float* __restrict__ g_out, tcsfm_frame_cfg cfg,
+__global__ void frame_bwd_prepare_kernel(const float* __restrict__ g_out, const float* __restrict__ g_total, tcsfm_frame_cfg cfg,
                                          float* __restrict__ g_scalars, float* __restrict__ g_min) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float gt = g_total ? g_total[0] : 0.f;
+    const float g_inv = (g_out ? g_out[0] : 0.f) + gt, g_fwd = (g_out ? g_out[1] : 0.f) + gt, g_dep = (g_out ? g_out[2] : 0.f) + gt;
     for (int g = 0; g < cfg.n_groups; ++g) {
-        g_scalars[g * 2 + 0] = (cfg.role[g] == 0) ? cfg.w_inverse * g_out[0] : 0.f;
-        g_scalars[g * 2 + 1] = cfg.w_depth * g_out[2];
+        g_scalars[g * 2 + 0] = (cfg.role[g] == 0) ? cfg.w_inverse * g_inv : 0.f;
+        g_scalars[g * 2 + 1] = cfg.w_depth * g_dep;
     }
-    g_min[0] = g_out[1] / (float)cfg.n_min_pixels;
+    g_min[0] = g_fwd / (float)cfg.n_min_pixels;
 }
 
 }  // namespace tcsfm
@@ -245,14 +249,16 @@ extern "C" int tcsfm_min_reduce(const float* base, int64_t stride, int count, in
     return check_launch("tcsfm_min_reduce");
 }
 
-extern "C" int tcsfm_frame_finalize(const float* sums, const float* min_sum, const tcsfm_frame_cfg* cfg, float* out, void* stream) {
+extern "C" int tcsfm_frame_finalize(const float* sums, const float* min_sum, const tcsfm_frame_cfg* cfg, float* out, float* total,
+                                    void* stream) {
     if (!sums || !cfg || !out || cfg->n_groups <= 0 || cfg->n_groups > 8) { set_error("tcsfm_frame_finalize: bad arguments"); return 1; }
-    TCSFM_LAUNCH(frame_finalize_kernel, dim3(1), dim3(32), 0, stream, sums, min_sum, *cfg, out);
+    TCSFM_LAUNCH(frame_finalize_kernel, dim3(1), dim3(32), 0, stream, sums, min_sum, *cfg, out, total);
     return check_launch("tcsfm_frame_finalize");
 }
 
-extern "C" int tcsfm_frame_bwd_prepare(const float* g_out, const tcsfm_frame_cfg* cfg, float* g_scalars, float* g_min, void* stream) {
-    if (!g_out || !cfg || !g_scalars || !g_min || cfg->n_groups <= 0 || cfg->n_groups > 8) { set_error("tcsfm_frame_bwd_prepare: bad arguments"); return 1; }
-    TCSFM_LAUNCH(frame_bwd_prepare_kernel, dim3(1), dim3(32), 0, stream, g_out, *cfg, g_scalars, g_min);
+extern "C" int tcsfm_frame_bwd_prepare(const float* g_out, const float* g_total, const tcsfm_frame_cfg* cfg, float* g_scalars,
+                                       float* g_min, void* stream) {
+    if ((!g_out && !g_total) || !cfg || !g_scalars || !g_min || cfg->n_groups <= 0 || cfg->n_groups > 8) { set_error("tcsfm_frame_bwd_prepare: bad arguments"); return 1; }
+    TCSFM_LAUNCH(frame_bwd_prepare_kernel, dim3(1), dim3(32), 0, stream, g_out, g_total, *cfg, g_scalars, g_min);
     return check_launch("tcsfm_frame_bwd_prepare");
 }

@@ -120,8 +120,8 @@ class Compute_Loss(nn.modules.Module):
         """All pair evaluations of one scale plus disp_to_depth, the pose algebra and the
         min-reprojection / mean-on-mask reductions as one fused autograd node.  `specs` are
         (tgt_img, ref_img, tgt_disp, ref_disp, pose) with full-resolution disparities and the
-        un-negated poses.  Returns the [3] tensor (l_reconstruct_inverse, l_reconstruct_forward,
-        l_depth)."""
+        un-negated poses.  Returns (terms [3], total [1]): (l_reconstruct_inverse,
+        l_reconstruct_forward, l_depth) and their sum."""
         images, disps = [], []
 
         def index(lst, t):
@@ -147,9 +147,11 @@ class Compute_Loss(nn.modules.Module):
                 validate=False, epoch=5, target_img_right=None):
         """Reference losses.py:75-140.  Returns the dict of [1]-shaped tensors
         l_reconstruct_inverse, l_reconstruct_forward, l_depth, l_smooth, total."""
-        zero = torch.zeros(1, dtype=intrinsics.dtype, device=intrinsics.device)   # (reference: torch.zeros(1).type_as)
-        losses = {'l_reconstruct_inverse': zero.clone(), 'l_reconstruct_forward': zero.clone(),
-                  'l_depth': zero.clone(), 'l_smooth': zero.clone()}
+        # (reference: four torch.zeros(1).type_as(intrinsics)); one fill, four one-element slices
+        zeros = torch.zeros(4, dtype=intrinsics.dtype, device=intrinsics.device)
+        keys = ('l_reconstruct_inverse', 'l_reconstruct_forward', 'l_depth', 'l_smooth')
+        losses = {key: zeros[i:i + 1] for i, key in enumerate(keys)}
+        fused_total = None              # (inverse + forward) + depth of a single fused scale, from the kernel
         disparity, source_disparities = disparity[0], disparity[1:]
         poses, poses_inv = poses[0], poses[1]
         _, _, h, w = target_img.size()
@@ -158,7 +160,7 @@ class Compute_Loss(nn.modules.Module):
             if scale != 0:
                 disp = nn.functional.interpolate(disp, (h, w), mode='nearest')
             if cfg['l_smooth']:
-                losses['l_smooth'] += (self.l_smooth_weight * get_smooth_loss(disp, target_img)) / (2 ** scale)
+                losses['l_smooth'] = losses['l_smooth'] + (self.l_smooth_weight * get_smooth_loss(disp, target_img)) / (2 ** scale)
             if cfg['l_reconstruction']:
                 # (tgt_img, ref_img, tgt_disp, ref_disp, pose); the pose handed to the warp is the
                 # negated prediction (losses.py:112,119) -- negated inside the fused node
@@ -168,17 +170,18 @@ class Compute_Loss(nn.modules.Module):
                     if scale != 0:
                         source_disparity = nn.functional.interpolate(source_disparity, (h, w), mode='nearest')
                     if cfg['l_smooth']:
-                        losses['l_smooth'] += (self.l_smooth_weight * get_smooth_loss(source_disparity, source_img)) / (2 ** scale)
+                        losses['l_smooth'] = losses['l_smooth'] + (self.l_smooth_weight * get_smooth_loss(source_disparity, source_img)) / (2 ** scale)
                     if cfg['l_inverse']:   # inverse reconstruction: target reprojected into the source frame
                         specs.append((source_img, target_img, source_disparity, disp, poses_inv[j]))
                         roles.append('inv')
                     specs.append((target_img, source_img, disp, source_disparity, poses[j]))
                     roles.append('fwd')
                 if self._can_fuse_frame(specs, intrinsics):
-                    terms = self._frame_terms(specs, roles, intrinsics)
+                    terms, total = self._frame_terms(specs, roles, intrinsics)
                     fresh = scale == 0          # 0 + x == x: skip the add into the zero tensor
-                    for i, key in enumerate(('l_reconstruct_inverse', 'l_reconstruct_forward', 'l_depth')):
+                    for i, key in enumerate(keys[:3]):
                         losses[key] = terms[i:i + 1] if fresh else losses[key] + terms[i:i + 1]
+                    fused_total = total if self.num_scales == 1 else None
                     continue
                 depth_of = {}
 
@@ -191,16 +194,21 @@ class Compute_Loss(nn.modules.Module):
                 reconstruction_errors = []
                 for role, (l_reprojection, l_depth, diff_img, _) in zip(roles, results):
                     if cfg['l_depth_consist']:
-                        losses['l_depth'] += self.l_depth_consist_weight * l_depth
+                        losses['l_depth'] = losses['l_depth'] + self.l_depth_consist_weight * l_depth
                     if role == 'inv':
-                        losses['l_reconstruct_inverse'] += 0.3 * l_reprojection
+                        losses['l_reconstruct_inverse'] = losses['l_reconstruct_inverse'] + 0.3 * l_reprojection
                     else:
                         reconstruction_errors.append(diff_img)
                 reconstruction_errors = torch.cat(reconstruction_errors, 1)
                 reconstruction_errors, _ = torch.min(reconstruction_errors, 1)
-                losses['l_reconstruct_forward'] += reconstruction_errors.mean()
+                losses['l_reconstruct_forward'] = losses['l_reconstruct_forward'] + reconstruction_errors.mean()
+        if fused_total is not None:
+            # total = ((inverse + forward) + depth) + smooth in the reference's order; the first two adds
+            # came out of the finalize kernel, x + 0 == x when the smoothness term is off
+            losses['total'] = fused_total + losses['l_smooth'] if cfg['l_smooth'] else fused_total
+            return losses
         losses['total'] = 0
-        for key in ('l_reconstruct_inverse', 'l_reconstruct_forward', 'l_depth', 'l_smooth'):
+        for key in keys:
             if self.num_scales != 1:               # x / 1 == x
                 losses[key] = losses[key] / (self.num_scales)
             losses['total'] = losses[key] if isinstance(losses['total'], int) else losses['total'] + losses[key]

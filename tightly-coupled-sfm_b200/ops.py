@@ -178,8 +178,10 @@ class FrameLossFn(torch.autograd.Function):
     groups, min-reprojection reduce and the mean-on-mask finalize forward; prepare, the pair
     kernel, the pose chain rule and the depth -> disparity chain rule backward.
 
-    apply(meta, kinv, K, *poses, *images, *disps) -> [3] = (l_reconstruct_inverse,
-    l_reconstruct_forward, l_depth) before the division by num_scales.
+    apply(meta, kinv, K, *poses, *images, *disps) -> (terms [3], total [1]):
+    terms = (l_reconstruct_inverse, l_reconstruct_forward, l_depth) before the division by
+    num_scales, total = (terms[0] + terms[1]) + terms[2] as Compute_Loss.forward adds them
+    (losses.py:134-138).  A loss built on `total` alone costs no slice / add kernels.
     meta: dict(w_l1, w_ssim, flags, w_inverse, w_depth, min_depth, max_depth, n_img,
     groups=[(role, tgt_img, ref_img, tgt_disp, ref_disp)]) with indices into `images` /
     `disps`; one pose [B,6] per group (un-negated); role 0 = inverse, 1 = forward."""
@@ -213,16 +215,20 @@ class FrameLossFn(torch.autograd.Function):
             if fwd_idx:
                 min_sum = _raw.min_reduce(lib(), diff[fwd_idx[0]], step * n_px, len(fwd_idx), n_px)
             cfg = _raw.make_frame_cfg([grp[0] for grp in groups], meta["w_inverse"], meta["w_depth"], n_px)
-            out = _raw.frame_finalize(lib(), sums, min_sum, cfg)
+            # two separate tensors (not views of one buffer): callers may add to `total` in place
+            terms, total = _raw.frame_finalize(lib(), sums, min_sum, cfg)
         if want_grad:
             ctx.save_for_backward(mask, sums, coef, diff, poses, K, *depths)
             ctx.batch, ctx.cfg, ctx.meta, ctx.flags = batch, cfg, meta, flags
             ctx.min_info = (fwd_idx, step * n_px)
             ctx.disp_range = max_disp - min_disp
-        return out
+            ctx.set_materialize_grads(False)
+        return terms, total
 
     @staticmethod
-    def backward(ctx, g_out):
+    def backward(ctx, g_terms, g_total):
+        if g_terms is None and g_total is None:
+            return (None,) * (3 + len(ctx.meta["groups"]) + ctx.meta["n_img"] + len(ctx.saved_tensors) - 6)
         mask, sums, coef, diff, poses, K = ctx.saved_tensors[:6]
         depths = list(ctx.saved_tensors[6:])
         meta, groups = ctx.meta, ctx.meta["groups"]
@@ -230,7 +236,7 @@ class FrameLossFn(torch.autograd.Function):
         fwd_idx, stride = ctx.min_info
         need_ref = (ctx.flags & (_cabi.DEPTH_MASK | _cabi.DEPTH_CONSIST)) != 0
         with _guard(K):
-            g_scalars, g_min = _raw.frame_bwd_prepare(lib(), g_out, ctx.cfg)
+            g_scalars, g_min = _raw.frame_bwd_prepare(lib(), g_terms, g_total, ctx.cfg)
             g_depths = torch.empty((len(depths),) + tuple(depths[0].shape), dtype=torch.float32, device=K.device)
             min_pos = [fwd_idx.index(i) if i in fwd_idx else -1 for i in range(g)]
             min_first = diff[fwd_idx[0]] if fwd_idx else None
