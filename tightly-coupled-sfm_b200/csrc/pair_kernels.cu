@@ -127,57 +127,89 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
     float own_mask[kPixPerThread], own_dd[kPixPerThread];
     // ---- phase A: own pixels.  The target depths head the longest dependent chain (depth ->
     //      projection -> tap addresses -> gathers), so all of a thread's are requested first. ----
-    int src_x[kPixPerThread + 1], src_y[kPixPerThread + 1];
-    bool src_ok[kPixPerThread + 1];
-    float src_depth[kPixPerThread + 1];
-#pragma unroll
-    for (int k = 0; k <= kPixPerThread; ++k) {
-        int cell;
-        if (k < kPixPerThread) cell = T1::cell(tx, ty0 + k);
-        else {                                         // the thread's halo-ring cell, if it has one
-            int cx = 0, cy = 0;
-            ring_cell(threadIdx.x < kRingCells ? threadIdx.x : 0, cx, cy);
-            cell = T1::cell(cx, cy);
-        }
-        // cells of a partial tile that lie outside the image hold the reflected pixel (or zero)
-        src_ok[k] = T1::cell_to_reflected(cell, x0, y0, H, W, src_y[k], src_x[k]) && (k < kPixPerThread || threadIdx.x < kRingCells);
-        src_depth[k] = src_ok[k] ? __ldg(c.tdep + src_y[k] * W + src_x[k]) : 1.0f;
-    }
+    // Own cells that no consumer reads (more than a pixel outside the image, partial tiles only) are
+    // filled like the others, from a clamped source pixel: the fills carry no control flow.
+    auto own_src = [&](int k, int& sx, int& sy) {
+        const int gy = y0 + ty0 + k;
+        sx = min(max(gx < W ? gx : 2 * W - 2 - gx, 0), W - 1);      // reflect1 for the one column / row past the edge
+        sy = min(max(gy < H ? gy : 2 * H - 2 - gy, 0), H - 1);
+    };
+    float src_depth[kPixPerThread];
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
-        const int gy = y0 + ty0 + k;
-        const int cell = T1::cell(tx, ty0 + k);
-        float m = 0.f, dd = 0.f;
-        bool valid = false;
-        const bool own = gx < W && gy < H;
-        if (src_ok[k]) fill_cell<F>(c, cam, A, src_x[k], src_y[k], src_depth[k], tw, T1::kCells, cell, need_depth && own, valid, dd);
-        else zero_cell(tw, T1::kCells, cell);
-        if (own) {
-            m = valid ? 1.f : 0.f;
-            if (auto_mask) {
-                const int pix = gy * W + gx;
-                float l1[3], ar[3];
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float2 v = tw[ch * T1::kCells + cell];
-                    l1[ch] = clamp01_nan(fabsf(__fsub_rn(v.x, v.y)));
-                    ar[ch] = fabsf(__fsub_rn(v.x, __ldg(c.ref + (ch * c.ref_sc + pix))));
-                }
-                if (!(mean3<F>(l1[0], l1[1], l1[2], A) < mean3<F>(ar[0], ar[1], ar[2], A))) m = 0.f;
-            }
-        }
-        own_mask[k] = m;
-        own_dd[k] = dd;
+        int sx, sy;
+        own_src(k, sx, sy);
+        src_depth[k] = __ldg(c.tdep + sy * W + sx);
     }
-    // ---- phase A': the halo ring (one cell per thread) ----
+    int ring_x = 0, ring_y = 0, ring_at = 0;          // the thread's halo-ring cell, if it has one
+    bool ring_ok = false;
+    float ring_depth = 1.0f;
     if (threadIdx.x < kRingCells) {
         int cx, cy;
         ring_cell(threadIdx.x, cx, cy);
-        const int cell = T1::cell(cx, cy);
+        ring_at = T1::cell(cx, cy);
+        ring_ok = T1::cell_to_reflected(ring_at, x0, y0, H, W, ring_y, ring_x);
+        if (ring_ok) ring_depth = __ldg(c.tdep + ring_y * W + ring_x);
+    }
+    // Two strip pixels at a time, staged by hand (geometry of both, then every gather of both, then
+    // the blends): ptxas keeps the cells strictly serial otherwise, because the IEEE-division slow
+    // paths are calls.  Cells no consumer reads are filled from a clamped source pixel (no branches).
+#pragma unroll
+    for (int k0 = 0; k0 < kPixPerThread; k0 += 2) {
+        WarpPt p[2];
+        TapIdx ti[2];
+        int pix[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            int sx, sy;
+            own_src(k0 + j, sx, sy);
+            pix[j] = sy * W + sx;
+            warp_point<F>(cam, A, sx, sy, src_depth[k0 + j], p[j]);
+            ti[j] = make_taps(p[j], H, W);
+        }
+        Taps tv[2][3], td[2];
+        float tg[2][3], rf[2][3];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                tv[j][ch] = load_taps(c.ref, ch * c.ref_sc, ti[j], W);
+                tg[j][ch] = __ldg(c.tgt + (ch * c.tgt_sc + pix[j]));
+                rf[j][ch] = auto_mask ? __ldg(c.ref + (ch * c.ref_sc + pix[j])) : 0.f;
+            }
+            if (need_depth) td[j] = load_taps(c.rdep, 0, ti[j], W);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int k = k0 + j, gy = y0 + ty0 + k;
+            const int cell = T1::cell(tx, ty0 + k);
+            const bool own = gx < W && gy < H;
+            float wv[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                wv[ch] = blend(tv[j][ch], ti[j]);
+                tw[ch * T1::kCells + cell] = make_float2(tg[j][ch], wv[ch]);
+            }
+            float m = (p[j].valid && own) ? 1.f : 0.f;
+            if (auto_mask) {
+                float l1[3], ar[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    l1[ch] = clamp01_nan(fabsf(__fsub_rn(tg[j][ch], wv[ch])));
+                    ar[ch] = fabsf(__fsub_rn(tg[j][ch], rf[j][ch]));
+                }
+                if (!(mean3<F>(l1[0], l1[1], l1[2], A) < mean3<F>(ar[0], ar[1], ar[2], A))) m = 0.f;
+            }
+            own_mask[k] = m;
+            own_dd[k] = (need_depth && own) ? depth_inconsistency(p[j].Z, blend(td[j], ti[j])) : 0.f;
+        }
+    }
+    // ---- phase A': the halo ring (one cell per thread) ----
+    if (threadIdx.x < kRingCells) {
         bool valid;
         float dd;
-        if (src_ok[kPixPerThread]) fill_cell<F>(c, cam, A, src_x[kPixPerThread], src_y[kPixPerThread], src_depth[kPixPerThread], tw, T1::kCells, cell, false, valid, dd);
-        else zero_cell(tw, T1::kCells, cell);
+        if (ring_ok) fill_cell<F>(c, cam, A, ring_x, ring_y, ring_depth, tw, T1::kCells, ring_at, false, valid, dd);
+        else zero_cell(tw, T1::kCells, ring_at);
     }
     __syncthreads();
 
