@@ -170,6 +170,19 @@ def test_bad_arguments_report_errors():
         _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, CPU | _cabi.SSIM | _cabi.DEPTH_MASK)
     with pytest.raises(RuntimeError, match="TCSFM_SSIM"):
         _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, CPU)
+    # in-kernel offsets inside one batch element are 32-bit: a channel stride that cannot be is refused
+    import ctypes
+    grp = _cabi.PairGroup()
+    dummy = torch.zeros(64)
+    for name in ("tgt_img", "ref_img", "tgt_depth", "kinv", "proj", "sums"):
+        setattr(grp, name, dummy.data_ptr())
+    grp.tgt_sc, grp.ref_sc = 64, 1 << 31
+    rc = emu().tcsfm_pair_loss_fwd(ctypes.byref(grp), 1, 1, 8, 8, 0.15, 0.85, CPU | _cabi.SSIM, None)
+    assert rc != 0 and b"channel stride out of range" in emu().tcsfm_last_error()
+    # the frame-level upstream needs at least one of its two gradient pointers
+    cfg = _raw.make_frame_cfg([0, 1], 0.3, 0.14, 64)
+    rc = emu().tcsfm_frame_bwd_prepare(None, None, ctypes.byref(cfg), dummy.data_ptr(), dummy.data_ptr(), None)
+    assert rc != 0 and b"tcsfm_frame_bwd_prepare" in emu().tcsfm_last_error()
 
 
 def test_pose_proj_fwd_bwd_vs_torch():
