@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 6
+#define TCSFM_ABI_VERSION 7
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -179,6 +179,15 @@ int tcsfm_disp_to_depth_fwd(const float* const* disp, float* const* depth, int c
                             float min_disp, float range, void* stream);
 int tcsfm_disp_to_depth_bwd(const float* const* g_depth, const float* const* depth, float* const* g_disp, int count,
                             int64_t n, float range, void* stream);
+
+/* The same with the nearest-neighbour upsample of a lower pyramid scale folded in
+ * (F.interpolate(disp, (H, W), mode='nearest') then disp_to_depth, losses.py:86-88,102-104): disp
+ * [B,1,h,w] -> depth [B,1,H,W] with ATen's index rule; the backward sums the gradients of the
+ * full-resolution pixels that read each low-resolution one: g_disp [B,1,h,w]. */
+int tcsfm_disp_upsample_to_depth_fwd(const float* const* disp, float* const* depth, int count, int B, int h, int w,
+                                     int H, int W, float min_disp, float range, void* stream);
+int tcsfm_disp_upsample_to_depth_bwd(const float* const* g_depth, const float* const* depth, float* const* g_disp,
+                                     int count, int B, int h, int w, int H, int W, float range, void* stream);
 
 /* out_sum[0] = sum_i min_j base[j*stride + i], j < count, i < n  (losses.py:129-131). */
 int tcsfm_min_reduce(const float* base, int64_t stride, int count, int64_t n, float* out_sum, void* stream);

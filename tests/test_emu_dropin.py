@@ -278,3 +278,32 @@ def test_l1_only_configuration_matches_oracle(emu_ops):
     (got[2].sum() + got[0]).backward()
     (ref[2].sum() + ref[0]).backward()
     assert rel_l2(d0.grad, d0r.grad) < 1e-4
+
+
+@pytest.mark.parametrize("smooth", [False, True])
+def test_compute_loss_multi_scale_vs_oracle(emu_ops, smooth):
+    """num_scales = 3 with the lower-scale disparities at their own resolution (losses.py:86-87,
+    102-103): the fused node upsamples inside its disp -> depth kernel."""
+    from oracle import ref_torch as O
+    from tcsfm_b200 import synth
+    fr = synth.make_frames(2, 24, 40, seed=3)
+    cfg = dict(goldens.LOSS_CFGS["full"], num_scales=3, l_smooth=smooth)
+    gen = torch.Generator().manual_seed(5)
+    sizes = [(24, 40), (12, 20), (5, 9)]
+    base = [[torch.nn.functional.interpolate(d, s, mode="bilinear", align_corners=False) if s != (24, 40) else d
+             for s in sizes] for d in fr["disps"]]
+    results = []
+    for impl in ("ours", "oracle"):
+        disps = [[leaf(t) for t in per_frame] for per_frame in base]
+        poses, poses_inv = [leaf(p) for p in fr["poses"]], [leaf(p) for p in fr["poses_inv"]]
+        args = (fr["sources"], fr["target"], [poses, poses_inv], disps, fr["K"])
+        out = losses.Compute_Loss(cfg)(*args) if impl == "ours" else O.compute_loss(cfg, *args)
+        out["total"].sum().backward()
+        grads = [t.grad if t.grad is not None else torch.zeros_like(t) for per_frame in disps for t in per_frame] + \
+                [t.grad if t.grad is not None else torch.zeros_like(t) for t in poses + poses_inv]
+        results.append(({k: float(v.detach()) for k, v in out.items()}, grads))
+    (la, ga), (lb, gb) = results
+    for k in lb:
+        assert abs(la[k] - lb[k]) <= 1e-5 * max(abs(lb[k]), 1e-12), (k, la[k], lb[k])
+    for a, b in zip(ga, gb):
+        assert a.shape == b.shape and rel_l2(a, b) < 1e-3

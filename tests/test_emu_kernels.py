@@ -244,3 +244,24 @@ def test_pair_and_photo_tiny_and_edge_sizes_vs_oracle(hw):
     (ref[1] * g1).sum().backward()
     g_rec, _, _ = _raw.photo_bwd(emu(), six[:, 0:3], rec, pd, cd, got[4], g1, None, 0.15, 0.85, CPU)
     assert rel_l2(g_rec, rec_l.grad) < 1e-4
+
+
+@pytest.mark.parametrize("shapes", [((47, 155), (376, 1242)), ((12, 20), (24, 40)), ((7, 9), (24, 40)), ((24, 40), (24, 40)),
+                                    ((1, 1), (5, 7)), ((94, 310), (376, 1242))])
+def test_disp_upsample_to_depth_vs_interpolate(shapes):
+    """The nearest upsample folded into disp -> depth (losses.py:86-88): bit for bit the index rule of
+    F.interpolate(mode='nearest'), and the gradient of the composed torch expression."""
+    (h, w), (big_h, big_w) = shapes
+    b = 2 if big_h < 100 else 1
+    gen = torch.Generator().manual_seed(h * 1000 + w)
+    disps = [torch.rand(b, 1, h, w, generator=gen).requires_grad_(True) for _ in range(3)]
+    min_disp, max_disp = 1 / 2.67, 1 / 0.06
+    got = _raw.disp_to_depth_fwd(emu(), [d.detach() for d in disps], min_disp, max_disp - min_disp, out_hw=(big_h, big_w))
+    g_out = [torch.randn(b, 1, big_h, big_w, generator=gen) for _ in range(3)]
+    g_got = _raw.disp_to_depth_bwd(emu(), g_out, got, max_disp - min_disp, disp_hw=(h, w))
+    for d, dep, g, gd in zip(disps, got, g_out, g_got):
+        up = torch.nn.functional.interpolate(d, (big_h, big_w), mode="nearest")
+        ref = 1 / (min_disp + (max_disp - min_disp) * up)
+        assert dep.shape == ref.shape and same(dep, ref)
+        ref.backward(g)
+        assert gd.shape == d.shape and rel_l2(gd, d.grad) < 1e-5

@@ -166,6 +166,33 @@ def test_compute_loss_vs_eager_cuda(shape, tag):
         assert rel_l2(grad(gpi[j]), grad(rpi[j])) < 1e-4, ("pose_inv", j, rel_l2(grad(gpi[j]), grad(rpi[j])))
 
 
+@pytest.mark.parametrize("hw", [(192, 640), (376, 1242), (100, 333)])
+def test_compute_loss_four_scales_vs_eager_cuda(hw):
+    """Config 5 (num_scales = 4): the lower-scale disparities arrive at their own resolution and are
+    nearest-upsampled inside the disp -> depth kernel; loss 1e-5, gradients (also of the low-resolution
+    disparities) 1e-4 against the reference's interpolate + disp_to_depth on the same GPU."""
+    h, w = hw
+    fr = frames(2, h, w, 0.0, synth.KITTI_DEPTH_RANGE, seed=11)
+    cfg = dict(goldens.LOSS_CFGS["full"], num_scales=4, min_depth=synth.KITTI_DEPTH_RANGE[0], max_depth=synth.KITTI_DEPTH_RANGE[1])
+    pyramid = [[d] + [torch.nn.functional.avg_pool2d(d, 2 ** sc, ceil_mode=True) for sc in range(1, 4)] for d in fr["disps"]]
+    res = []
+    for impl in ("oracle", "cuda"):
+        disps = [[leaf(t) for t in per_frame] for per_frame in pyramid]
+        poses, poses_inv = [leaf(p) for p in fr["poses"]], [leaf(p) for p in fr["poses_inv"]]
+        args = (fr["sources"], fr["target"], [poses, poses_inv], disps, fr["K"])
+        out = O.compute_loss(cfg, *args) if impl == "oracle" else losses.Compute_Loss(cfg)(*args)
+        out["total"].sum().backward()
+        res.append((out, [t for per_frame in disps for t in per_frame] + poses + poses_inv))
+    (ro, rl), (go, gl) = res
+    for k in ("l_reconstruct_inverse", "l_reconstruct_forward", "l_depth", "total"):
+        a, bb = float(go[k].detach()), float(ro[k].detach())
+        assert abs(a - bb) <= 1e-5 * max(abs(bb), 1e-12), (k, a, bb)
+    for i, (a, bb) in enumerate(zip(gl, rl)):
+        ga = a.grad if a.grad is not None else torch.zeros_like(a)
+        gb = bb.grad if bb.grad is not None else torch.zeros_like(bb)
+        assert ga.shape == gb.shape and rel_l2(ga, gb) < 1e-4, (i, tuple(a.shape), rel_l2(ga, gb))
+
+
 @pytest.mark.parametrize("shape", SHAPES[:3])
 def test_pair_masks_bit_exact_vs_eager_cuda(shape):
     b, h, w, yaw, rng = shape

@@ -2,7 +2,7 @@
 package loader and by the test-only emulator binding)."""
 import ctypes as C
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 ARITH_CPU = 1 << 0
 AUTO_MASK = 1 << 1
@@ -62,6 +62,10 @@ SIGNATURES = {
                                           C.c_float, C.c_float, C.c_void_p]),
     "tcsfm_disp_to_depth_bwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
                                           _i64, C.c_float, C.c_void_p]),
+    "tcsfm_disp_upsample_to_depth_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
+                                                   C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "tcsfm_disp_upsample_to_depth_bwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
+                                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "tcsfm_min_reduce": (C.c_int, [_fp, _i64, C.c_int, _i64, _fp, C.c_void_p]),
     "tcsfm_frame_finalize": (C.c_int, [_fp, _fp, C.POINTER(FrameCfg), _fp, _fp, C.c_void_p]),
     "tcsfm_frame_bwd_prepare": (C.c_int, [_fp, _fp, C.POINTER(FrameCfg), _fp, _fp, C.c_void_p]),

@@ -337,24 +337,48 @@ def _ptr_table(tensors):
     return arr
 
 
-def disp_to_depth_fwd(lib, disps, min_disp, disp_range):
-    """disps: list of <= 4 equally shaped fp32 maps -> list of depth maps (one launch)."""
+def disp_to_depth_fwd(lib, disps, min_disp, disp_range, out_hw=None):
+    """disps: list of <= 4 equally shaped fp32 maps [B,1,h,w] -> list of depth maps (one launch).
+    With out_hw = (H, W) != (h, w) the nearest-neighbour upsample of losses.py:86-87 is folded in:
+    the depths come out at [B,1,H,W]."""
     disps = [_f32c(d, "disp") for d in disps]
-    depths = [torch.empty_like(d) for d in disps]
-    with _timing.launch("disp_to_depth_fwd", disps[0].is_cuda):
-        rc = lib.tcsfm_disp_to_depth_fwd(_ptr_table(disps), _ptr_table(depths), len(disps), disps[0].numel(),
-                                         min_disp, disp_range, _stream(disps[0]))
+    b, h, w = disps[0].shape[0], disps[0].shape[-2], disps[0].shape[-1]
+    if any(d.shape != disps[0].shape for d in disps):
+        raise ValueError("disp_to_depth_fwd: the maps of one launch must share a shape")
+    if out_hw is None or tuple(out_hw) == (h, w):
+        depths = [torch.empty_like(d) for d in disps]
+        with _timing.launch("disp_to_depth_fwd", disps[0].is_cuda):
+            rc = lib.tcsfm_disp_to_depth_fwd(_ptr_table(disps), _ptr_table(depths), len(disps), disps[0].numel(),
+                                             min_disp, disp_range, _stream(disps[0]))
+    else:
+        if disps[0].dim() != 4 or disps[0].shape[1] != 1:
+            raise ValueError("disp_to_depth_fwd: upsampling expects [B,1,h,w] maps")
+        big_h, big_w = int(out_hw[0]), int(out_hw[1])
+        depths = [torch.empty((b, 1, big_h, big_w), dtype=torch.float32, device=d.device) for d in disps]
+        with _timing.launch("disp_to_depth_fwd", disps[0].is_cuda):
+            rc = lib.tcsfm_disp_upsample_to_depth_fwd(_ptr_table(disps), _ptr_table(depths), len(disps), b, h, w, big_h, big_w,
+                                                      min_disp, disp_range, _stream(disps[0]))
     _cabi.check(lib, rc)
     _timing.count_launch()
     return depths
 
 
-def disp_to_depth_bwd(lib, g_depths, depths, disp_range):
+def disp_to_depth_bwd(lib, g_depths, depths, disp_range, disp_hw=None):
+    """Gradients w.r.t. the disparities; disp_hw = (h, w) of the disparity maps when they were
+    upsampled by disp_to_depth_fwd (the gradient comes out at that resolution)."""
     g_depths = [_f32c(g, "g_depth") for g in g_depths]
-    g_disps = [torch.empty_like(d) for d in depths]
-    with _timing.launch("disp_to_depth_bwd", depths[0].is_cuda):
-        rc = lib.tcsfm_disp_to_depth_bwd(_ptr_table(g_depths), _ptr_table(depths), _ptr_table(g_disps), len(depths),
-                                         depths[0].numel(), disp_range, _stream(depths[0]))
+    b, big_h, big_w = depths[0].shape[0], depths[0].shape[-2], depths[0].shape[-1]
+    if disp_hw is None or tuple(disp_hw) == (big_h, big_w):
+        g_disps = [torch.empty_like(d) for d in depths]
+        with _timing.launch("disp_to_depth_bwd", depths[0].is_cuda):
+            rc = lib.tcsfm_disp_to_depth_bwd(_ptr_table(g_depths), _ptr_table(depths), _ptr_table(g_disps), len(depths),
+                                             depths[0].numel(), disp_range, _stream(depths[0]))
+    else:
+        h, w = int(disp_hw[0]), int(disp_hw[1])
+        g_disps = [torch.empty((b, 1, h, w), dtype=torch.float32, device=d.device) for d in depths]
+        with _timing.launch("disp_to_depth_bwd", depths[0].is_cuda):
+            rc = lib.tcsfm_disp_upsample_to_depth_bwd(_ptr_table(g_depths), _ptr_table(depths), _ptr_table(g_disps), len(depths),
+                                                      b, h, w, big_h, big_w, disp_range, _stream(depths[0]))
     _cabi.check(lib, rc)
     _timing.count_launch()
     return g_disps

@@ -147,6 +147,60 @@ disp_to_depth_bwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float ran
     }
 }
 
+// The same with the nearest-neighbour upsample of the lower pyramid scales folded in
+// (Compute_Loss.forward, losses.py:86-88,102-104: F.interpolate(disp, (H, W), mode='nearest') then
+// disp_to_depth).  ATen's rule: src = min(int(floorf(dst * scale)), in - 1), scale = float(in) / out.
+struct UpShape { int B, h, w, H, W; float sh, sw; };
+
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+    const int s = (int)floorf(__fmul_rn((float)dst, scale));
+    return s < in_size - 1 ? s : in_size - 1;
+}
+
+__global__ void __launch_bounds__(256)
+disp_up_to_depth_fwd_kernel(const __grid_constant__ MapPtrs M, UpShape U, float min_disp, float range) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t plane = (int64_t)U.H * U.W;
+    if (i >= U.B * plane) return;
+    const int b = (int)(i / plane);
+    const int r = (int)(i - b * plane);
+    const int Y = r / U.W, X = r - Y * U.W;
+    const int64_t src = ((int64_t)b * U.h + nearest_src(Y, U.sh, U.h)) * U.w + nearest_src(X, U.sw, U.w);
+    for (int k = 0; k < M.count; ++k) {
+        const float scaled = __fadd_rn(__fmul_rn(__ldg(M.in[k] + src), range), min_disp);
+        M.out[k][i] = __frcp_rn(scaled);
+    }
+}
+
+// One thread per low-resolution pixel gathers the gradients of the full-resolution pixels that read it.
+__global__ void __launch_bounds__(256)
+disp_up_to_depth_bwd_kernel(const __grid_constant__ MapPtrs M, UpShape U, float range) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t plane = (int64_t)U.h * U.w;
+    if (i >= U.B * plane) return;
+    const int b = (int)(i / plane);
+    const int r = (int)(i - b * plane);
+    const int y = r / U.w, x = r - y * U.w;
+    // candidate destination ranges (one extra on each side), filtered with the forward's own rule
+    int Y0 = (int)floorf((float)y / U.sh) - 1, Y1 = (int)ceilf((float)(y + 1) / U.sh) + 1;
+    int X0 = (int)floorf((float)x / U.sw) - 1, X1 = (int)ceilf((float)(x + 1) / U.sw) + 1;
+    Y0 = Y0 < 0 ? 0 : Y0; X0 = X0 < 0 ? 0 : X0;
+    Y1 = Y1 > U.H - 1 ? U.H - 1 : Y1; X1 = X1 > U.W - 1 ? U.W - 1 : X1;
+    for (int k = 0; k < M.count; ++k) {
+        float acc = 0.f;
+        for (int Y = Y0; Y <= Y1; ++Y) {
+            if (nearest_src(Y, U.sh, U.h) != y) continue;
+            const int64_t row = ((int64_t)b * U.H + Y) * U.W;
+            for (int X = X0; X <= X1; ++X) {
+                if (nearest_src(X, U.sw, U.w) != x) continue;
+                const float d = __ldg(M.aux[k] + row + X);
+                acc += -__ldg(M.in[k] + row + X) * d * d * range;
+            }
+        }
+        M.out[k][i] = acc;
+    }
+}
+
 constexpr int kReduceThreads = 256;
 
 __global__ void __launch_bounds__(kReduceThreads)
@@ -237,6 +291,39 @@ extern "C" int tcsfm_disp_to_depth_bwd(const float* const* g_depth, const float*
     for (int k = 0; k < count; ++k) { M.in[k] = g_depth[k]; M.aux[k] = depth[k]; M.out[k] = g_disp[k]; }
     TCSFM_LAUNCH(disp_to_depth_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, M, n, range);
     return check_launch("tcsfm_disp_to_depth_bwd");
+}
+
+static bool up_shape(UpShape& U, int B, int h, int w, int H, int W) {
+    if (B <= 0 || h <= 0 || w <= 0 || H < h || W < w) return false;
+    U.B = B; U.h = h; U.w = w; U.H = H; U.W = W;
+    U.sh = (float)h / (float)H; U.sw = (float)w / (float)W;          // ATen compute_scales_value<float>
+    return true;
+}
+
+extern "C" int tcsfm_disp_upsample_to_depth_fwd(const float* const* disp, float* const* depth, int count, int B, int h, int w,
+                                                int H, int W, float min_disp, float range, void* stream) {
+    UpShape U;
+    if (!disp || !depth || count < 1 || count > 4 || !up_shape(U, B, h, w, H, W)) { set_error("tcsfm_disp_upsample_to_depth_fwd: bad arguments"); return 1; }
+    MapPtrs M;
+    memset(&M, 0, sizeof(M));
+    M.count = count;
+    for (int k = 0; k < count; ++k) { M.in[k] = disp[k]; M.out[k] = depth[k]; }
+    const int64_t n = (int64_t)B * H * W;
+    TCSFM_LAUNCH(disp_up_to_depth_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, M, U, min_disp, range);
+    return check_launch("tcsfm_disp_upsample_to_depth_fwd");
+}
+
+extern "C" int tcsfm_disp_upsample_to_depth_bwd(const float* const* g_depth, const float* const* depth, float* const* g_disp,
+                                                int count, int B, int h, int w, int H, int W, float range, void* stream) {
+    UpShape U;
+    if (!g_depth || !depth || !g_disp || count < 1 || count > 4 || !up_shape(U, B, h, w, H, W)) { set_error("tcsfm_disp_upsample_to_depth_bwd: bad arguments"); return 1; }
+    MapPtrs M;
+    memset(&M, 0, sizeof(M));
+    M.count = count;
+    for (int k = 0; k < count; ++k) { M.in[k] = g_depth[k]; M.aux[k] = depth[k]; M.out[k] = g_disp[k]; }
+    const int64_t n = (int64_t)B * h * w;
+    TCSFM_LAUNCH(disp_up_to_depth_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, M, U, range);
+    return check_launch("tcsfm_disp_upsample_to_depth_bwd");
 }
 
 extern "C" int tcsfm_min_reduce(const float* base, int64_t stride, int count, int64_t n, float* out_sum, void* stream) {

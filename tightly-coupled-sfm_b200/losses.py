@@ -114,13 +114,15 @@ class Compute_Loss(nn.modules.Module):
     def _can_fuse_frame(self, specs, intrinsics):
         return (self.config['l_ssim'] == True and not intrinsics.requires_grad      # noqa: E712
                 and len(specs) <= 8
-                and all(s[0].shape == specs[0][0].shape and s[1].shape == specs[0][0].shape for s in specs))
+                and all(s[0].shape == specs[0][0].shape and s[1].shape == specs[0][0].shape for s in specs)
+                # disparities [B,1,h,w] of one scale share a resolution (possibly lower than the images')
+                and all(s[k].dim() == 4 and s[k].shape == specs[0][2].shape for s in specs for k in (2, 3)))
 
     def _frame_terms(self, specs, roles, intrinsics):
         """All pair evaluations of one scale plus disp_to_depth, the pose algebra and the
         min-reprojection / mean-on-mask reductions as one fused autograd node.  `specs` are
-        (tgt_img, ref_img, tgt_disp, ref_disp, pose) with full-resolution disparities and the
-        un-negated poses.  Returns (terms [3], total [1]): (l_reconstruct_inverse,
+        (tgt_img, ref_img, tgt_disp, ref_disp, pose) with the disparities at their own pyramid
+        resolution and the un-negated poses.  Returns (terms [3], total [1]): (l_reconstruct_inverse,
         l_reconstruct_forward, l_depth) and their sum."""
         images, disps = [], []
 
@@ -156,21 +158,29 @@ class Compute_Loss(nn.modules.Module):
         poses, poses_inv = poses[0], poses[1]
         _, _, h, w = target_img.size()
         cfg = self.config
+        upsampled = {}
+
+        def full_res(dmap):
+            """losses.py:86-87,102-103: the lower scales are nearest-upsampled to the image size.  The fused
+            frame node reads them at their own resolution (the upsample is folded into its disp -> depth
+            kernel); only the smoothness term and the composed fall-back need the upsampled tensor."""
+            if tuple(dmap.shape[-2:]) == (h, w):
+                return dmap
+            if id(dmap) not in upsampled:
+                upsampled[id(dmap)] = nn.functional.interpolate(dmap, (h, w), mode='nearest')
+            return upsampled[id(dmap)]
+
         for scale, disp in enumerate(disparity):
-            if scale != 0:
-                disp = nn.functional.interpolate(disp, (h, w), mode='nearest')
             if cfg['l_smooth']:
-                losses['l_smooth'] = losses['l_smooth'] + (self.l_smooth_weight * get_smooth_loss(disp, target_img)) / (2 ** scale)
+                losses['l_smooth'] = losses['l_smooth'] + (self.l_smooth_weight * get_smooth_loss(full_res(disp), target_img)) / (2 ** scale)
             if cfg['l_reconstruction']:
                 # (tgt_img, ref_img, tgt_disp, ref_disp, pose); the pose handed to the warp is the
                 # negated prediction (losses.py:112,119) -- negated inside the fused node
                 specs, roles = [], []
                 for j, source_img in enumerate(source_imgs):
                     source_disparity = source_disparities[j][scale]
-                    if scale != 0:
-                        source_disparity = nn.functional.interpolate(source_disparity, (h, w), mode='nearest')
                     if cfg['l_smooth']:
-                        losses['l_smooth'] = losses['l_smooth'] + (self.l_smooth_weight * get_smooth_loss(source_disparity, source_img)) / (2 ** scale)
+                        losses['l_smooth'] = losses['l_smooth'] + (self.l_smooth_weight * get_smooth_loss(full_res(source_disparity), source_img)) / (2 ** scale)
                     if cfg['l_inverse']:   # inverse reconstruction: target reprojected into the source frame
                         specs.append((source_img, target_img, source_disparity, disp, poses_inv[j]))
                         roles.append('inv')
@@ -183,6 +193,7 @@ class Compute_Loss(nn.modules.Module):
                         losses[key] = terms[i:i + 1] if fresh else losses[key] + terms[i:i + 1]
                     fused_total = total if self.num_scales == 1 else None
                     continue
+                specs = [(s_[0], s_[1], full_res(s_[2]), full_res(s_[3]), s_[4]) for s_ in specs]
                 depth_of = {}
 
                 def to_depth(dmap):

@@ -196,9 +196,12 @@ class FrameLossFn(torch.autograd.Function):
         min_disp, max_disp = 1 / meta["max_depth"], 1 / meta["min_depth"]      # learning_helpers.py:82-83
         with _guard(K):
             kinv = kinv.contiguous()
+            # disparities of a lower pyramid scale arrive at their own resolution: the nearest upsample of
+            # losses.py:86-87,102-103 happens inside the disp -> depth kernel
+            full_hw = tuple(images[0].shape[-2:])
             depths = []
             for i in range(0, len(disps), 4):
-                depths += _raw.disp_to_depth_fwd(lib(), disps[i:i + 4], min_disp, max_disp - min_disp)
+                depths += _raw.disp_to_depth_fwd(lib(), disps[i:i + 4], min_disp, max_disp - min_disp, out_hw=full_hw)
             poses = torch.cat([p[:, 0:6] for p in poses_in], 0)
             proj = _raw.pose_proj_fwd(lib(), poses, K, -1.0, pose_flags(b))
             specs = [{"tgt_img": images[ti], "ref_img": images[ri], "tgt_depth": depths[td], "ref_depth": depths[rd],
@@ -222,6 +225,7 @@ class FrameLossFn(torch.autograd.Function):
             ctx.batch, ctx.cfg, ctx.meta, ctx.flags = batch, cfg, meta, flags
             ctx.min_info = (fwd_idx, step * n_px)
             ctx.disp_range = max_disp - min_disp
+            ctx.disp_hw = tuple(disps[0].shape[-2:])
             ctx.set_materialize_grads(False)
         return terms, total
 
@@ -248,7 +252,7 @@ class FrameLossFn(torch.autograd.Function):
             g_disps = []
             for i in range(0, len(depths), 4):
                 g_disps += _raw.disp_to_depth_bwd(lib(), [g_depths[j] for j in range(i, min(i + 4, len(depths)))],
-                                                  depths[i:i + 4], ctx.disp_range)
+                                                  depths[i:i + 4], ctx.disp_range, disp_hw=ctx.disp_hw)
         g_poses = tuple(g_pose[i * b:(i + 1) * b] for i in range(g))
         return (None, None, None) + g_poses + (None,) * meta["n_img"] + tuple(g_disps)
 
