@@ -8,21 +8,27 @@
 // Forward (64x16 tile, 256 threads, a vertical strip of 4 pixels per thread):
 //   A. each thread back-projects / projects its pixels (the CTA also the 1-pixel halo
 //      ring), gathers the 4 bilinear taps of the 3 source channels and stores
-//      (target, warped) as one float2 per cell of a shared-memory tile;
+//      (target, warped) as one float2 per cell of a shared-memory tile.  Two strip pixels
+//      are staged together (geometry of both, every gather of both, then the blends) so
+//      that their load latencies overlap;
 //   C. per channel a thread slides a 3x3 register window down its strip: one LDS.64 per
 //      tap, squares/products once per tap, and the five avg_pool2d-ordered running sums
 //      as packed fp32x2 adds; /9 is an exact 3-instruction sequence.  L1, auto-mask,
 //      SSIM, depth-consistency weight, block-reduced masked sums (3 atomics per CTA).
 //   When a backward pass will follow, the SSIM adjoint coefficients (3 per channel) are
-//   written next to diff_img/mask (36 B/px of workspace) so that the backward neither
+//   written next to diff_img/mask (40 B/px of workspace) so that the backward neither
 //   re-warps a 2-pixel halo nor recomputes window statistics.
 //
-// Backward (same tiling): stage upstream-scaled coefficients of the +1 ring in shared
-// memory, gather each own pixel's 3x3 coefficient neighbourhood as separable rolling
-// sums (reflection = two conditional extra terms), add the L1 / depth-consistency
-// adjoints and push the result through the bilinear + projective adjoint: grad(target
-// depth) is a direct store, grad(source depth) a 4-tap atomic scatter, grad(K[R|t]) 12
-// block-reduced accumulators per batch element.
+// Backward (same tiling), three phases with disjoint register working sets:
+//   B. cp.async the nine coefficient planes of the tile + 1 ring into shared memory next
+//      to the per-cell upstream gradient (explicit grad + masked-mean term + per-pixel min
+//      routing); cells with a zero upstream are zero-filled without reading HBM;
+//   C. separable rolling 3x3 sums of coefficient x upstream (reflection = two conditional
+//      extra terms) reduce to the line g_w = P + w * Q per channel; (P, Q) and the own
+//      depth replace the coefficients of the thread's own cells;
+//   D. per own pixel: L1 / depth-consistency adjoints, then the bilinear + projective
+//      adjoint: grad(target depth) is a direct store, grad(source depth) a 4-tap atomic
+//      scatter, grad(K[R|t]) 12 block-reduced accumulators per batch element.
 #include "tile.cuh"
 
 namespace tcsfm {
@@ -32,10 +38,8 @@ namespace tcsfm {
 #define TCSFM_FWD_MIN_BLOCKS 3
 #endif
 #ifndef TCSFM_BWD_MIN_BLOCKS
-#define TCSFM_BWD_MIN_BLOCKS 4      // measured: 4 CTAs/SM with ~200 B of spills beats 2-3 CTAs/SM without (latency bound)
+#define TCSFM_BWD_MIN_BLOCKS 4      // measured: 4 CTAs/SM (64 registers, 24 B of spills) beats 3 CTAs/SM without spills by 9 %
 #endif
-
-
 #ifndef TCSFM_BWD_D_UNROLL
 #define TCSFM_BWD_D_UNROLL 2      // measured: 2 overlaps two pixels' gather chains (-3%), 4 spills
 #endif
