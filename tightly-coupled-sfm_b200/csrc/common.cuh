@@ -79,6 +79,18 @@ __device__ __forceinline__ void async_copy4(float* smem_dst, const float* src, b
 #endif
 }
 
+// The same for four consecutive floats (both addresses 16-byte aligned); .cg: streamed once, L2 only.
+__device__ __forceinline__ void async_copy16(float* smem_dst, const float* src, bool live) {
+#ifdef TCSFM_HOST_EMU
+    for (int i = 0; i < 4; ++i) smem_dst[i] = live ? src[i] : 0.f;
+#else
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t"
+                 "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t}"
+                 :: "r"(dst), "l"(src), "r"((unsigned)live) : "memory");
+#endif
+}
+
 // Block-wide sum of N per-thread partials -> one atomicAdd per value per block.
 // `red` is shared scratch of at least N * (threads/32) floats.  All threads of
 // the block must call this (it contains __syncthreads()).

@@ -53,6 +53,7 @@ struct PairLaunch {
     Arith A;
     float w_l1, w_ssim, C1, C2;
     int flags;
+    int vec16;                       // backward: every coefficient row start is 16-byte aligned (W % 4 == 0, aligned base)
 };
 
 struct PairCtx {
@@ -333,12 +334,32 @@ __device__ __forceinline__ float upstream_diff(const tcsfm_pair_group& g, const 
     return Gd;
 }
 
+// Out-of-line copy for the rare layouts (more than two min-reprojection candidates): keeps the
+// staging code of the common case small.
+__device__ __noinline__ float upstream_diff_generic(const tcsfm_pair_group& g, const BwdScalars& sc, const float* gdiff,
+                                                    int64_t bn, int pix, float m) {
+    return upstream_diff(g, sc, gdiff, bn, pix, m);
+}
+
+// Backward tile: row pitch 68 floats with the interior starting at column 4, so that the 64 interior
+// cells of a row are 16-byte aligned in shared memory and go global -> shared as 16 cp.async of 16
+// bytes instead of 64 of 4.  The left halo sits at column 3, the right halo of row r in the (otherwise
+// unused) column 0 of row r + 1; hence the 4 trailing floats.
+struct BwdTile {
+    static constexpr int kPitch = kTileW + 4;
+    static constexpr int kRows = kTileH + 2;
+    static constexpr int kCells = kPitch * kRows + 4;                 // floats per plane
+    static constexpr int kLogical = (kTileW + 2) * kRows;             // cells that exist
+    __device__ __forceinline__ static int cell(int cx, int cy) { return (cy + 1) * kPitch + cx + 4; }
+};
+constexpr size_t kBwdSmemBytes = 10 * BwdTile::kCells * sizeof(float);
+static_assert(4 * (kBwdSmemBytes + 1024) <= 196 * 1024, "four backward CTAs must fit the 196 KB shared-memory carve-out");
+
 template <int F>
 __global__ void __launch_bounds__(kTileThreads, TCSFM_BWD_MIN_BLOCKS)
 pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
-    using T1 = Tile<1>;
-    TCSFM_DYN_SMEM(float, cs);                     // [9][T1::kCells] coefficients, [kCells] upstream, [own] depth upstream
-    TCSFM_SHARED float red[12 * (kTileThreads / 32)];
+    using BT = BwdTile;
+    TCSFM_DYN_SMEM(float, cs);                     // [9][BT::kCells] coefficients, [BT::kCells] upstream gradient
 
     const tcsfm_pair_group& g = L.g[blockIdx.z];
     const Arith& A = L.A;
@@ -364,52 +385,100 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     // ---- phase B: the nine coefficient planes of the tile + 1 ring go global -> shared with
     //      cp.async (no register staging, all loads in flight at once; zero fill outside the
     //      image), next to the upstream gradient of diff_img at each ring pixel ----
-    float* Gs = cs + 9 * T1::kCells;               // [cells] upstream gradient (0 outside the image)
-    constexpr int kStageIters = (T1::kCells + kTileThreads - 1) / kTileThreads;
-    // pass 1: request everything the upstream gradient of this thread's cells depends on (branch
-    // free, so that the loads of all cells are in flight together); pass 2: combine and copy
-    int st_pix[kStageIters];
-    float st_m[kStageIters], st_g[kStageIters], st_v[kStageIters], st_o[kStageIters];
+    float* Gs = cs + 9 * BT::kCells;               // [cells] upstream gradient (0 outside the image)
     const bool two_way = sc.min_other != nullptr;                    // per-pixel min over exactly two sources
+    // Upstream gradient of one pixel from its loaded ingredients (mask, explicit grad, own / other
+    // min-reprojection candidate); torch.min(dim): the first index holding the minimum wins, a NaN is the minimum.
+    auto combine = [&](int pix, float m, float gd, float v, float o) {
+        if (!two_way && sc.min_self) return upstream_diff_generic(g, sc, gdiff, (int64_t)b * n, pix, m);
+        float Gd = sc.c_rep * m + gd;
+        const bool win = (g.min_index == 1) ? !(o <= v || o != o) : !(o < v || (o != o && v == v));
+        if (two_way && win) Gd += sc.g_min;
+        return Gd;
+    };
+    if (L.vec16) {
+        // Rows are 16-byte aligned: a task is four interior cells of one row (288 tasks) or one halo
+        // cell (36 tasks).  Its thread loads mask / gradient / candidates as float4, forms the four
+        // upstream values and issues one 16-byte cp.async per coefficient plane.  A chunk is read
+        // when any of its cells has a non-zero upstream (dead cells multiply by zero later); masked-out
+        // pixels of the inverse groups and the losing source of the per-pixel min skip their 36 B/px.
+        constexpr int kChunkTasks = BT::kRows * (kTileW / 4), kTasks = kChunkTasks + 2 * BT::kRows;
+        auto stage_task = [&](int task) {
+            if (task < kChunkTasks) {
+                const int row = task / (kTileW / 4), chunk = task - row * (kTileW / 4);
+                const int qy = y0 + row - 1, qx = x0 + 4 * chunk;
+                const bool inside = qy >= 0 && qy < H && qx < W;
+                const int pix = inside ? qy * W + qx : 0;                // pixel 0 stands in: always a valid address
+                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mask + pix));
+                const float4 g4 = gdiff ? __ldg(reinterpret_cast<const float4*>(gdiff + pix)) : zero4;
+                const float4 v4 = two_way ? __ldg(reinterpret_cast<const float4*>(sc.min_self + pix)) : zero4;
+                const float4 o4 = two_way ? __ldg(reinterpret_cast<const float4*>(sc.min_other + pix)) : zero4;
+                float4 G4 = zero4;
+                if (inside) {
+                    G4.x = combine(pix, m4.x, g4.x, v4.x, o4.x);
+                    G4.y = combine(pix + 1, m4.y, g4.y, v4.y, o4.y);
+                    G4.z = combine(pix + 2, m4.z, g4.z, v4.z, o4.z);
+                    G4.w = combine(pix + 3, m4.w, g4.w, v4.w, o4.w);
+                }
+                const int at = row * BT::kPitch + 4 + 4 * chunk;
+                *reinterpret_cast<float4*>(Gs + at) = G4;
+                const bool live = (G4.x != 0.f) || (G4.y != 0.f) || (G4.z != 0.f) || (G4.w != 0.f);
 #pragma unroll
-    for (int it = 0; it < kStageIters; ++it) {
-        const int cell = threadIdx.x + it * kTileThreads;
-        int cx, cy;
-        T1::cell_xy(cell < T1::kCells ? cell : 0, cx, cy);
-        const int qx = x0 + cx, qy = y0 + cy;
-        const bool inside = cell < T1::kCells && qx >= 0 && qx < W && qy >= 0 && qy < H;
-        const int pix = inside ? qy * W + qx : 0;                    // pixel 0 stands in: always a valid address
-        st_pix[it] = inside ? pix : -1;
-        st_m[it] = __ldg(mask + pix);
-        st_g[it] = gdiff ? __ldg(gdiff + pix) : 0.f;
-        st_v[it] = two_way ? __ldg(sc.min_self + pix) : 0.f;
-        st_o[it] = two_way ? __ldg(sc.min_other + pix) : 0.f;
-    }
-#pragma unroll
-    for (int it = 0; it < kStageIters; ++it) {
-        const int cell = threadIdx.x + it * kTileThreads;
-        if (cell >= T1::kCells) break;
-        const bool inside = st_pix[it] >= 0;
-        const int pix = inside ? st_pix[it] : 0;
-        float Gd = 0.f;
-        if (inside) {
-            if (two_way || !sc.min_self) {
-                Gd = sc.c_rep * st_m[it] + st_g[it];
-                // torch.min(dim): the first index holding the minimum wins; a NaN is the minimum
-                const float v = st_v[it], o = st_o[it];
-                const bool win = (g.min_index == 1) ? !(o <= v || o != o) : !(o < v || (o != o && v == v));
-                if (two_way && win) Gd += sc.g_min;
+                for (int j = 0; j < 9; ++j) async_copy16(cs + j * BT::kCells + at, coef + (j * n + pix), live);
             } else {
-                Gd = upstream_diff(g, sc, gdiff, (int64_t)b * n, pix, st_m[it]);
-            }
-        }
-        // coefficients only matter where the upstream gradient is non-zero (masked-out pixels of
-        // the inverse groups, the losing source of the per-pixel min): skip their 36 B/px
-        const bool live = Gd != 0.f;
+                const int h2 = task - kChunkTasks;
+                const int row = h2 >> 1, cx = (h2 & 1) ? kTileW : -1;
+                const int qy = y0 + row - 1, qx = x0 + cx;
+                const bool inside = qy >= 0 && qy < H && qx >= 0 && qx < W;
+                const int pix = inside ? qy * W + qx : 0;
+                float Gd = 0.f;
+                if (inside) Gd = combine(pix, __ldg(mask + pix), gdiff ? __ldg(gdiff + pix) : 0.f,
+                                         two_way ? __ldg(sc.min_self + pix) : 0.f, two_way ? __ldg(sc.min_other + pix) : 0.f);
+                const int at = BT::cell(cx, row - 1);
+                Gs[at] = Gd;
+                const bool live = Gd != 0.f;
 #pragma unroll
-        for (int j = 0; j < 9; ++j)
-            async_copy4(cs + j * T1::kCells + cell, coef + (j * n + pix), live);
-        Gs[cell] = Gd;
+                for (int j = 0; j < 9; ++j) async_copy4(cs + j * BT::kCells + at, coef + (j * n + pix), live);
+            }
+        };
+        stage_task(threadIdx.x);
+        if (threadIdx.x + kTileThreads < kTasks) stage_task(threadIdx.x + kTileThreads);
+    } else {
+        // unaligned rows (W % 4 != 0): one cell at a time, all loads of a thread's cells requested first
+        constexpr int kStageIters = (BT::kLogical + kTileThreads - 1) / kTileThreads;
+        int st_pix[kStageIters];
+        float st_m[kStageIters], st_g[kStageIters], st_v[kStageIters], st_o[kStageIters];
+        auto logical_xy = [&](int l, int& cx, int& cy) { cy = l / (kTileW + 2); cx = l - cy * (kTileW + 2) - 1; cy -= 1; };
+#pragma unroll
+        for (int it = 0; it < kStageIters; ++it) {
+            const int l = threadIdx.x + it * kTileThreads;
+            int cx, cy;
+            logical_xy(l < BT::kLogical ? l : 0, cx, cy);
+            const int qx = x0 + cx, qy = y0 + cy;
+            const bool inside = l < BT::kLogical && qx >= 0 && qx < W && qy >= 0 && qy < H;
+            const int pix = inside ? qy * W + qx : 0;
+            st_pix[it] = inside ? pix : -1;
+            st_m[it] = __ldg(mask + pix);
+            st_g[it] = gdiff ? __ldg(gdiff + pix) : 0.f;
+            st_v[it] = two_way ? __ldg(sc.min_self + pix) : 0.f;
+            st_o[it] = two_way ? __ldg(sc.min_other + pix) : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < kStageIters; ++it) {
+            const int l = threadIdx.x + it * kTileThreads;
+            if (l >= BT::kLogical) break;
+            int cx, cy;
+            logical_xy(l, cx, cy);
+            const int cell = BT::cell(cx, cy);
+            const bool inside = st_pix[it] >= 0;
+            const int pix = inside ? st_pix[it] : 0;
+            const float Gd = inside ? combine(pix, st_m[it], st_g[it], st_v[it], st_o[it]) : 0.f;
+            Gs[cell] = Gd;
+            const bool live = Gd != 0.f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) async_copy4(cs + j * BT::kCells + cell, coef + (j * n + pix), live);
+        }
     }
     __pipeline_commit();
     __pipeline_wait_prior(0);
@@ -432,12 +501,12 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         float h[3][9];
         const bool dup_l = (gx == 1), dup_r = (gx == W - 2);
         auto hsum = [&](int r, float (&out)[9]) {          // horizontal 3-sums of tile row ty0 - 1 + r
-            const int c1 = T1::cell(tx, ty0 - 1 + r);
+            const int c1 = BT::cell(tx, ty0 - 1 + r);
             // upstream of the three neighbours; a border neighbour that is folded back counts twice
             const float gl = Gs[c1 - 1] * (dup_l ? 2.f : 1.f), gm = Gs[c1], gr = Gs[c1 + 1] * (dup_r ? 2.f : 1.f);
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
-                const float* pl = cs + j * T1::kCells + c1;
+                const float* pl = cs + j * BT::kCells + c1;
                 out[j] = pl[-1] * gl + pl[0] * gm + pl[1] * gr;
             }
         };
@@ -471,9 +540,9 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
 #pragma unroll
         for (int k = 0; k < kPixPerThread; ++k)
 #pragma unroll
-            for (int j = 0; j < 6; ++j) cs[j * T1::kCells + T1::cell(tx, ty0 + k)] = pq[k][j];
+            for (int j = 0; j < 6; ++j) cs[j * BT::kCells + BT::cell(tx, ty0 + k)] = pq[k][j];
 #pragma unroll
-        for (int k = 0; k < kPixPerThread; ++k) cs[6 * T1::kCells + T1::cell(tx, ty0 + k)] = dep_own[k];
+        for (int k = 0; k < kPixPerThread; ++k) cs[6 * BT::kCells + BT::cell(tx, ty0 + k)] = dep_own[k];
     }
 
     // ---- phase D, one own pixel at a time: L1 / depth adjoints and the geometry adjoint ----
@@ -485,8 +554,8 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         const int gy = y0 + ty0 + k;
         if (gx < W && gy < H) {
             const int pix = gy * W + gx;
-            const int cell = T1::cell(tx, ty0 + k);
-            const float dep = cs[6 * T1::kCells + cell], m = __ldg(mask + pix);
+            const int cell = BT::cell(tx, ty0 + k);
+            const float dep = cs[6 * BT::kCells + cell], m = __ldg(mask + pix);
             const float d0 = depth_mask ? __ldg(coef + (9 * n + pix)) : 0.f;
             WarpPt p;
             warp_point<F>(cam, A, gx, gy, dep, p);
@@ -510,7 +579,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
                 const float w = blend(tv, ti);
                 const float t = __ldg(c.tgt + (ch * c.tgt_sc + pix));
                 const float dlt = t - w;
-                float gwc = cs[(2 * ch) * T1::kCells + cell] + w * cs[(2 * ch + 1) * T1::kCells + cell];
+                float gwc = cs[(2 * ch) * BT::kCells + cell] + w * cs[(2 * ch + 1) * BT::kCells + cell];
                 if (fabsf(dlt) <= 1.0f) gwc += (dlt > 0.f) ? -gl1 : ((dlt < 0.f) ? gl1 : 0.f);
                 bilinear_grad(tv, p, gwc, g_ix, g_iy);
             }
@@ -534,7 +603,8 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             }
         }
     }
-    if (g.g_proj) block_atomic_accumulate<12>(acc, red, g.g_proj + b * 12, threadIdx.x, kTileThreads);
+    __syncthreads();                                   // phase D is over everywhere: the tile doubles as reduction scratch
+    if (g.g_proj) block_atomic_accumulate<12>(acc, cs, g.g_proj + b * 12, threadIdx.x, kTileThreads);
 }
 
 static int fill_launch(PairLaunch& L, const tcsfm_pair_group* groups, int n, int B, int H, int W,
@@ -598,7 +668,7 @@ extern "C" int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
 extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
                                    float w_l1, float w_ssim, int flags, void* stream) {
     if (!groups || n_groups <= 0) { set_error("tcsfm_pair_loss_bwd: no groups"); return 1; }
-    const size_t smem = 10 * Tile<1>::kCells * sizeof(float);
+    const size_t smem = kBwdSmemBytes;
     const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
     for (int base = 0; base < n_groups; base += kMaxGroups) {
         const int n = (n_groups - base < kMaxGroups) ? n_groups - base : kMaxGroups;
@@ -618,6 +688,12 @@ extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
             cudaMemsetAsync(L.g[i].g_proj, 0, (size_t)(j - i) * B * 12 * sizeof(float), (cudaStream_t)stream);
             i = j;
         }
+        // 16-byte staging needs every row start of the planes it reads aligned
+        auto aligned16 = [](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % 16 == 0; };
+        L.vec16 = (W % 4 == 0);
+        for (int i = 0; i < n; ++i)
+            L.vec16 = L.vec16 && aligned16(L.g[i].coef) && aligned16(L.g[i].mask) && aligned16(L.g[i].g_diff) &&
+                      aligned16(L.g[i].min_base) && L.g[i].min_stride % 4 == 0;
         dim3 grid(tiles, B, n), block(kTileThreads);
         TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(pair_bwd_kernel<F>, grid, block, smem, stream, L));
         if (int rc = check_launch("tcsfm_pair_loss_bwd")) return rc;
