@@ -389,11 +389,13 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     const bool two_way = sc.min_other != nullptr;                    // per-pixel min over exactly two sources
     // Upstream gradient of one pixel from its loaded ingredients (mask, explicit grad, own / other
     // min-reprojection candidate); torch.min(dim): the first index holding the minimum wins, a NaN is the minimum.
+    const bool many_way = sc.min_self && g.min_count > 2;            // rare: out of line
+    const bool one_way = sc.min_self && g.min_count == 1;            // a single source always holds the minimum
     auto combine = [&](int pix, float m, float gd, float v, float o) {
-        if (!two_way && sc.min_self) return upstream_diff_generic(g, sc, gdiff, (int64_t)b * n, pix, m);
+        if (many_way) return upstream_diff_generic(g, sc, gdiff, (int64_t)b * n, pix, m);
         float Gd = sc.c_rep * m + gd;
         const bool win = (g.min_index == 1) ? !(o <= v || o != o) : !(o < v || (o != o && v == v));
-        if (two_way && win) Gd += sc.g_min;
+        if (one_way || (two_way && win)) Gd += sc.g_min;
         return Gd;
     };
     if (L.vec16) {
