@@ -1,5 +1,6 @@
 #!/bin/bash
 # Times the pair kernels (and the whole step) for every tuning build under build/.
+shopt -s nullglob
 for lib in default build/libtcsfm_*.so; do
   if [ "$lib" != default ]; then export TCSFM_B200_LIB=$PWD/$lib; else unset TCSFM_B200_LIB; fi
   python bench.py --steps 60 --warmup 10 --no-cpu-baseline > gpurun_out/bench_var.json 2> gpurun_out/bench_var.err || tail -3 gpurun_out/bench_var.err
