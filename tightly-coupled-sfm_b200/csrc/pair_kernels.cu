@@ -45,10 +45,6 @@ namespace tcsfm {
 #endif
 constexpr int kBwdDUnroll = TCSFM_BWD_D_UNROLL;
 
-#ifndef TCSFM_FWD_ROLL_CH
-#define TCSFM_FWD_ROLL_CH 0
-#endif
-
 constexpr int kMaxGroups = 8;
 constexpr int kCoefPlanes = 10;      // 3 channels x (A, B, C) + the un-weighted photometric error
 
@@ -225,13 +221,7 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
     // ---- phase C: 3x3 statistics down the strip, one channel at a time ----
     float esum[kPixPerThread];
     float* coef_base = pin_pointer(g.coef ? g.coef + (int64_t)b * kCoefPlanes * n : nullptr);   // offsets below: < 2^31 (fill_launch)
-#if TCSFM_FWD_ROLL_CH
 #pragma unroll
-    for (int k = 0; k < kPixPerThread; ++k) esum[k] = 0.f;          // 0 + e == e exactly
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
     for (int ch = 0; ch < 3; ++ch) {
         const float2* plane = tw + ch * T1::kCells;
         // rolling 3-row window of (target, warped) taps; squares / products are formed per use
@@ -258,11 +248,7 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
             const float2 ctr = wv[4];
             const float l1 = clamp01_nan(fabsf(__fsub_rn(ctr.x, ctr.y)));
             const float e = __fadd_rn(__fmul_rn(l1, L.w_l1), __fmul_rn(clamp01_nan(t.raw), L.w_ssim));
-#if TCSFM_FWD_ROLL_CH
-            esum[k] = __fadd_rn(esum[k], e);
-#else
             esum[k] = (ch == 0) ? e : __fadd_rn(esum[k], e);
-#endif
             const int gy = y0 + ty0 + k;
             if (coef_base && gx < W && gy < H) {
                 // d diff / d ssim_c = (1 - dd) * (1/3) * w_ssim ; the backward multiplies by its upstream
