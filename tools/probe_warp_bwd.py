@@ -1,5 +1,7 @@
+"""Times the standalone inverse_warp2 backward (tcsfm_warp_bwd) at B=24 192x640 with and without the
+source-depth / source-image gradient scatters; used with tools/probe_variants_ops.sh to A/B tuning builds."""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from tcsfm_b200 import _raw, stn, synth
 from tcsfm_b200._lib import lib
 L = lib(); dev = torch.device('cuda:0'); b, h, w = 24, 192, 640
