@@ -501,15 +501,23 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     {
         float pq[kPixPerThread][6];
         float h[3][9];
-        const bool dup_l = (gx == 1), dup_r = (gx == W - 2);
+        // The three cells (c-1, c, c+1) of a row are read as one aligned 8-byte pair and one single:
+        // even columns pair (c, c+1) and take c-1 alone, odd columns pair (c-1, c) and take c+1 alone
+        // (two shared-memory wavefronts per warp instead of three).  The upstream weights are permuted
+        // to match; a border neighbour that reflection folds back counts twice.
+        const int par = tx & 1;
+        const float dup_l = (gx == 1) ? 2.f : 1.f, dup_r = (gx == W - 2) ? 2.f : 1.f;
+        const float f_a = par ? dup_l : 1.f, f_b = par ? 1.f : dup_r, f_c = par ? dup_r : dup_l;
+        const int single_at = par ? 2 : -1;                  // offset of the single cell from the pair
         auto hsum = [&](int r, float (&out)[9]) {          // horizontal 3-sums of tile row ty0 - 1 + r
-            const int c1 = BT::cell(tx, ty0 - 1 + r);
-            // upstream of the three neighbours; a border neighbour that is folded back counts twice
-            const float gl = Gs[c1 - 1] * (dup_l ? 2.f : 1.f), gm = Gs[c1], gr = Gs[c1 + 1] * (dup_r ? 2.f : 1.f);
+            const int c0 = BT::cell(tx, ty0 - 1 + r) - par;  // even: the pair starts at the centre cell
+            const float2 gp = *reinterpret_cast<const float2*>(Gs + c0);
+            const float wa = gp.x * f_a, wb = gp.y * f_b, wc = Gs[c0 + single_at] * f_c;
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
-                const float* pl = cs + j * BT::kCells + c1;
-                out[j] = pl[-1] * gl + pl[0] * gm + pl[1] * gr;
+                const float* pl = cs + j * BT::kCells + c0;
+                const float2 pr = *reinterpret_cast<const float2*>(pl);
+                out[j] = pr.x * wa + pr.y * wb + pl[single_at] * wc;
             }
         };
         hsum(0, h[1]);
