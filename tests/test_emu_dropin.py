@@ -356,3 +356,27 @@ def test_compute_loss_switches_vs_oracle(emu_ops, overrides):
         assert abs(la[k] - lb[k]) <= 1e-5 * max(abs(lb[k]), 1e-12), (k, la[k], lb[k])
     for a, b in zip(ga, gb):
         assert rel_l2(a, b) < 1e-3 or (a.abs().max() == 0 and b.abs().max() == 0)
+
+
+def test_compute_loss_three_sources_vs_oracle(emu_ops):
+    """Three source frames: six pair groups in one launch and a three-way per-pixel min (the
+    out-of-line routing path of the backward)."""
+    from oracle import ref_torch as O
+    from tcsfm_b200 import synth
+    fr = synth.make_frames(2, 24, 40, n_src=3, seed=12)
+    cfg = goldens.LOSS_CFGS["full"]
+    results = []
+    for impl in ("ours", "oracle"):
+        disps = [[leaf(d)] for d in fr["disps"]]
+        poses, poses_inv = [leaf(p) for p in fr["poses"]], [leaf(p) for p in fr["poses_inv"]]
+        args = (fr["sources"], fr["target"], [poses, poses_inv], disps, fr["K"])
+        out = losses.Compute_Loss(cfg)(*args) if impl == "ours" else O.compute_loss(cfg, *args)
+        out["total"].sum().backward()
+        leaves = [d[0] for d in disps] + poses + poses_inv
+        results.append(({k: float(v.detach()) for k, v in out.items()},
+                        [t.grad if t.grad is not None else torch.zeros_like(t) for t in leaves]))
+    (la, ga), (lb, gb) = results
+    for k in lb:
+        assert abs(la[k] - lb[k]) <= 1e-5 * max(abs(lb[k]), 1e-12), (k, la[k], lb[k])
+    for a, b in zip(ga, gb):
+        assert rel_l2(a, b) < 1e-3

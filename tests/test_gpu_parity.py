@@ -216,6 +216,31 @@ def test_compute_loss_large_frames_and_batches_vs_eager_cuda(shape):
         assert rel_l2(ga, gb) < 1e-4, (i, tuple(a.shape), rel_l2(ga, gb))
 
 
+@pytest.mark.parametrize("shape", [(4, 192, 640), (3, 90, 130)])
+def test_compute_loss_three_sources_vs_eager_cuda(shape):
+    """Three source frames: six pair groups per launch, three-way per-pixel min-reprojection."""
+    b, h, w = shape
+    fr = synth.make_frames(b, h, w, n_src=3, seed=41, depth_range=synth.KITTI_DEPTH_RANGE, device=DEV,
+                           intrinsics=synth.scaled_intrinsics(h, w))
+    cfg = dict(goldens.LOSS_CFGS["full"], min_depth=synth.KITTI_DEPTH_RANGE[0], max_depth=synth.KITTI_DEPTH_RANGE[1])
+    res = []
+    for impl in ("oracle", "cuda"):
+        disps = [[leaf(d)] for d in fr["disps"]]
+        poses, poses_inv = [leaf(p) for p in fr["poses"]], [leaf(p) for p in fr["poses_inv"]]
+        args = (fr["sources"], fr["target"], [poses, poses_inv], disps, fr["K"])
+        out = O.compute_loss(cfg, *args) if impl == "oracle" else losses.Compute_Loss(cfg)(*args)
+        out["total"].sum().backward()
+        res.append((out, [d[0] for d in disps] + poses + poses_inv))
+    (ro, rl), (go, gl) = res
+    for k in ("l_reconstruct_inverse", "l_reconstruct_forward", "l_depth", "total"):
+        a, bb = float(go[k].detach()), float(ro[k].detach())
+        assert abs(a - bb) <= 1e-5 * max(abs(bb), 1e-12), (k, a, bb)
+    for i, (a, bb) in enumerate(zip(gl, rl)):
+        ga = a.grad if a.grad is not None else torch.zeros_like(a)
+        gb = bb.grad if bb.grad is not None else torch.zeros_like(bb)
+        assert rel_l2(ga, gb) < 1e-4, (i, tuple(a.shape), rel_l2(ga, gb))
+
+
 @pytest.mark.parametrize("hw", [(192, 640), (376, 1242), (100, 333)])
 def test_compute_loss_four_scales_vs_eager_cuda(hw):
     """Config 5 (num_scales = 4): the lower-scale disparities arrive at their own resolution and are
