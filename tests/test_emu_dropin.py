@@ -380,3 +380,84 @@ def test_compute_loss_three_sources_vs_oracle(emu_ops):
         assert abs(la[k] - lb[k]) <= 1e-5 * max(abs(lb[k]), 1e-12), (k, la[k], lb[k])
     for a, b in zip(ga, gb):
         assert rel_l2(a, b) < 1e-3
+
+
+# ---- regressions for the round-1 review findings ------------------------------------------------
+
+def test_two_scales_with_num_scales_one_matches_oracle(emu_ops):
+    """A caller may hand more disparity scales than config['num_scales'] says: the reference iterates over
+    every entry of `disparity` (losses.py:84) and divides by num_scales (losses.py:136), so `total` must be
+    the sum over all passed scales (the fused per-scale total is only valid for a single scale)."""
+    from oracle import ref_torch as O
+    g = Golden(goldens.CASES[0])
+    fr = g.frames()
+    cfg = goldens.LOSS_CFGS["full"]
+    low = [torch.nn.functional.avg_pool2d(d, 2) for d in fr["disps"]]
+    outs = []
+    for impl in ("ours", "oracle"):
+        disps = [[leaf(d), leaf(l)] for d, l in zip(fr["disps"], low)]
+        args = (fr["sources"], fr["target"], [fr["poses"], fr["poses_inv"]], disps, fr["K"])
+        out = losses.Compute_Loss(cfg)(*args) if impl == "ours" else O.compute_loss(cfg, *args)
+        out["total"].sum().backward()
+        outs.append((out, [t.grad for ds in disps for t in ds]))
+    for k in ("l_reconstruct_inverse", "l_reconstruct_forward", "l_depth", "total"):
+        a, b = float(outs[0][0][k]), float(outs[1][0][k])
+        assert abs(a - b) <= 1e-5 * abs(b), (k, a, b)
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert rel_l2(a, b) < 1e-3
+
+
+def test_eight_wide_pose_vectors(emu_ops):
+    """check_sizes accepts [B,8] poses (models/stn.py:252); the gradient comes back [B,8] with zeros in the
+    two unused columns."""
+    g = Golden(goldens.CASES[0])
+    fr = g.frames()
+    cfg = goldens.LOSS_CFGS["full"]
+
+    def run(widen):
+        pad = (lambda p: torch.cat([p, torch.ones(p.shape[0], 2)], 1)) if widen else (lambda p: p)
+        poses, poses_inv = [leaf(pad(p)) for p in fr["poses"]], [leaf(pad(p)) for p in fr["poses_inv"]]
+        disps = [leaf(d) for d in fr["disps"]]
+        out = losses.Compute_Loss(cfg)(fr["sources"], fr["target"], [poses, poses_inv], [[d] for d in disps], fr["K"])
+        out["total"].sum().backward()
+        return float(out["total"]), poses[0].grad
+    v6, g6 = run(False)
+    v8, g8 = run(True)
+    assert v6 == v8 and g8.shape == (g6.shape[0], 8)
+    assert torch.equal(g8[:, 0:6], g6) and float(g8[:, 6:].abs().sum()) == 0
+
+
+def test_shape_mismatches_are_rejected(emu_ops):
+    """Depth / intrinsics tensors that do not match the images must raise instead of being read out of bounds."""
+    g = Golden(goldens.CASES[0])
+    fr = g.frames()
+    mod = losses.Compute_Loss(goldens.LOSS_CFGS["full"])
+    small = fr["depths"][0][:, :, ::2, ::2].contiguous()
+    with pytest.raises(ValueError, match="tgt_depth"):
+        mod.compute_pairwise_loss(fr["target"], fr["sources"][0], small, fr["depths"][1], -fr["poses"][0], fr["K"], 0)
+    with pytest.raises(ValueError, match="ref_depth"):
+        mod.compute_pairwise_loss(fr["target"], fr["sources"][0], fr["depths"][0], small, -fr["poses"][0], fr["K"], 0)
+    with pytest.raises((ValueError, RuntimeError)):
+        mod.compute_pairwise_loss(fr["target"], fr["sources"][0], fr["depths"][0], fr["depths"][1], -fr["poses"][0],
+                                  fr["K"][:1], 0)
+
+
+def test_image_gradients_are_refused(emu_ops):
+    g = Golden(goldens.CASES[0])
+    fr = g.frames()
+    mod = losses.Compute_Loss(goldens.LOSS_CFGS["full"])
+    with pytest.raises(NotImplementedError, match="images"):
+        mod.compute_pairwise_loss(leaf(fr["target"]), fr["sources"][0], fr["depths"][0], fr["depths"][1],
+                                  -fr["poses"][0], fr["K"], 0)
+    with pytest.raises(NotImplementedError, match="images"):
+        mod(fr["sources"], leaf(fr["target"]), [fr["poses"], fr["poses_inv"]], [[d] for d in fr["disps"]], fr["K"])
+
+
+def test_intrinsics_inverse_is_never_stale():
+    """K^-1 is recomputed per call (models/stn.py:257): views and in-place edits of K must be honoured."""
+    k = torch.tensor([[[370.7, 0.3, 313.1], [0.1, 367.1, 94.6], [0.0, 0.0, 1.0]]]).repeat(2, 1, 1)
+    a = stn.inverse_intrinsics(k)
+    assert torch.equal(a, k.inverse())
+    assert torch.equal(stn.inverse_intrinsics(k.transpose(1, 2)), k.transpose(1, 2).inverse())
+    k.data[:, 0, 0] = 500.0
+    assert torch.equal(stn.inverse_intrinsics(k), k.inverse())

@@ -46,10 +46,23 @@ def image_view(img, name="img"):
     return img, (img.stride(0) if b > 1 else c * h * w), (img.stride(1) if c > 1 else h * w)
 
 
+def _expect(t, shape, name):
+    """The kernels index raw pointers: a wrongly shaped tensor would be read out of bounds, so every
+    marshalling helper checks the shapes the reference's own operators would have rejected."""
+    if t is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (name, list(shape), list(t.shape)))
+
+
 def warp_fwd(lib, img, depth, ref_depth, kinv, proj, flags=0, need_depths=True, stack_target=None):
     """stack_target: optional [B,3,H,W] view of the reconstruction target; when given the kernel
     also writes the next pose-network input [target * valid | projected_img] ([B,6,H,W])."""
     b, _, h, w = img.shape
+    _expect(img, (b, 3, h, w), "img")
+    _expect(depth, (b, 1, h, w), "depth")
+    _expect(ref_depth, (b, 1, h, w), "ref_depth")
+    _expect(kinv, (b, 3, 3), "kinv")
+    _expect(proj, (b, 3, 4), "proj")
+    _expect(stack_target, (b, 3, h, w), "stack_target")
     img, sb, sc = image_view(img)
     depth, ref_depth = _f32c(depth, "depth"), _f32c(ref_depth, "ref_depth")
     kinv, proj = _f32c(kinv, "kinv"), _f32c(proj, "proj")
@@ -75,6 +88,15 @@ def warp_fwd(lib, img, depth, ref_depth, kinv, proj, flags=0, need_depths=True, 
 def warp_bwd(lib, img, depth, ref_depth, kinv, proj, g_img, g_pd, g_cd, flags=0,
              need_img_grad=False, need_ref_depth_grad=True, g_stack=None):
     b, _, h, w = img.shape
+    _expect(img, (b, 3, h, w), "img")
+    _expect(depth, (b, 1, h, w), "depth")
+    _expect(ref_depth, (b, 1, h, w), "ref_depth")
+    _expect(kinv, (b, 3, 3), "kinv")
+    _expect(proj, (b, 3, 4), "proj")
+    _expect(g_img, (b, 3, h, w), "g_img")
+    _expect(g_pd, (b, 1, h, w), "g_pd")
+    _expect(g_cd, (b, 1, h, w), "g_cd")
+    _expect(g_stack, (b, 6, h, w), "g_stack")
     img, sb, sc = image_view(img)
     depth, ref_depth = _f32c(depth, "depth"), _f32c(ref_depth, "ref_depth")
     kinv, proj = _f32c(kinv, "kinv"), _f32c(proj, "proj")
@@ -135,6 +157,11 @@ class PairBatch:
         for i, g in enumerate(groups):
             if g["tgt_img"].shape != first.shape or g["ref_img"].shape != first.shape:
                 raise ValueError("all pair groups of one launch must share [B,3,H,W]")
+            _expect(first, (self.b, 3, self.h, self.w), "tgt_img")
+            _expect(g["tgt_depth"], (self.b, 1, self.h, self.w), "tgt_depth")
+            _expect(g.get("ref_depth"), (self.b, 1, self.h, self.w), "ref_depth")
+            _expect(g["kinv"], (self.b, 3, 3), "kinv")
+            _expect(g["proj"], (self.b, 3, 4), "proj")
             tgt, tsb, tsc = image_view(g["tgt_img"], "tgt_img")
             ref, rsb, rsc = image_view(g["ref_img"], "ref_img")
             td, rd = _f32c(g["tgt_depth"], "tgt_depth"), _f32c(g.get("ref_depth"), "ref_depth")
@@ -298,6 +325,10 @@ def pair_loss_bwd_shared(lib, batch, mask, sums, coef, g_scalars, g_min, min_inf
 
 def photo_fwd(lib, tgt, src, rec, proj_depth, comp_depth, w_l1, w_ssim, flags=0, want_grad=True):
     n, _, h, w = rec.shape
+    for t, name in ((tgt, "tgt"), (src, "src"), (rec, "rec")):
+        _expect(t, (n, 3, h, w), name)
+    _expect(proj_depth, (n, 1, h, w), "proj_depth")
+    _expect(comp_depth, (n, 1, h, w), "comp_depth")
     tgt, tsb, tsc = image_view(tgt, "tgt")
     src, ssb, ssc = image_view(src, "src")
     rec, pd, cd = _f32c(rec, "rec"), _f32c(proj_depth, "proj_depth"), _f32c(comp_depth, "comp_depth")

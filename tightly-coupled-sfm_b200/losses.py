@@ -74,11 +74,18 @@ class Compute_Loss(nn.modules.Module):
         self.l_depth_consist_weight = config['l_depth_consist_weight']
 
     # -- fused evaluation of a list of (tgt_img, ref_img, tgt_depth, ref_depth, pose) pairs
+    @staticmethod
+    def _refuse_image_grads(specs):
+        if any(s[0].requires_grad or s[1].requires_grad for s in specs):
+            raise NotImplementedError("gradients w.r.t. the images are not implemented by the fused pair loss "
+                                      "(no reference call site differentiates them)")
+
     def _pair_groups(self, specs, intrinsics):
         """One launch for all `specs`.  Returns per-group (l_reprojection, l_depth,
         diff_img, valid_mask)."""
         if intrinsics.requires_grad:
             raise NotImplementedError("gradients w.r.t. the intrinsics are not implemented")
+        self._refuse_image_grads(specs)
         if self.config['l_ssim'] != True:   # noqa: E712
             # L1-only configuration (diff_img keeps its 3 channels, losses.py:154,180): composed from the
             # fused warp; no reference script runs it, so it gets no dedicated kernel
@@ -118,7 +125,7 @@ class Compute_Loss(nn.modules.Module):
                 # disparities [B,1,h,w] of one scale share a resolution (possibly lower than the images')
                 and all(s[k].dim() == 4 and s[k].shape == specs[0][2].shape for s in specs for k in (2, 3)))
 
-    def _frame_terms(self, specs, roles, intrinsics):
+    def _frame_terms(self, specs, roles, intrinsics, kinv):
         """All pair evaluations of one scale plus disp_to_depth, the pose algebra and the
         min-reprojection / mean-on-mask reductions as one fused autograd node.  `specs` are
         (tgt_img, ref_img, tgt_disp, ref_disp, pose) with the disparities at their own pyramid
@@ -142,8 +149,9 @@ class Compute_Loss(nn.modules.Module):
                 "w_depth": float(self.l_depth_consist_weight) if want_depth else 0.0,
                 "min_depth": self.config['min_depth'], "max_depth": self.config['max_depth'],
                 "n_img": len(images), "groups": groups}
-        return ops.FrameLossFn.apply(meta, inverse_intrinsics(intrinsics), intrinsics,
-                                     *[s[4] for s in specs], *images, *disps)
+        # check_sizes accepts [B,8] pose vectors (models/stn.py:252); only the first six enter the warp
+        poses = [s[4] if s[4].shape[1] == 6 else s[4][:, 0:6] for s in specs]
+        return ops.FrameLossFn.apply(meta, kinv, intrinsics, *poses, *images, *disps)
 
     def forward(self, source_imgs, target_img, poses, disparity, intrinsics, pose_vec_weight=None,
                 validate=False, epoch=5, target_img_right=None):
@@ -154,6 +162,10 @@ class Compute_Loss(nn.modules.Module):
         keys = ('l_reconstruct_inverse', 'l_reconstruct_forward', 'l_depth', 'l_smooth')
         losses = {key: zeros[i:i + 1] for i, key in enumerate(keys)}
         fused_total = None              # (inverse + forward) + depth of a single fused scale, from the kernel
+        # the kernel's sum is the whole `total` only when this call evaluates exactly one scale and divides
+        # by one (the reference loops over every entry of `disparity` whatever num_scales says, losses.py:84,136)
+        single_scale = len(disparity[0]) == 1 and self.num_scales == 1
+        kinv = None
         disparity, source_disparities = disparity[0], disparity[1:]
         poses, poses_inv = poses[0], poses[1]
         _, _, h, w = target_img.size()
@@ -187,11 +199,14 @@ class Compute_Loss(nn.modules.Module):
                     specs.append((target_img, source_img, disp, source_disparity, poses[j]))
                     roles.append('fwd')
                 if self._can_fuse_frame(specs, intrinsics):
-                    terms, total = self._frame_terms(specs, roles, intrinsics)
+                    self._refuse_image_grads(specs)
+                    if kinv is None:
+                        kinv = inverse_intrinsics(intrinsics)            # models/stn.py:257, once per call
+                    terms, total = self._frame_terms(specs, roles, intrinsics, kinv)
                     fresh = scale == 0          # 0 + x == x: skip the add into the zero tensor
                     for i, key in enumerate(keys[:3]):
                         losses[key] = terms[i:i + 1] if fresh else losses[key] + terms[i:i + 1]
-                    fused_total = total if self.num_scales == 1 else None
+                    fused_total = total if single_scale else None
                     continue
                 specs = [(s_[0], s_[1], full_res(s_[2]), full_res(s_[3]), s_[4]) for s_ in specs]
                 depth_of = {}

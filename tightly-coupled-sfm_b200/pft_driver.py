@@ -143,14 +143,12 @@ class WindowRunner:
         return loss
 
     def _set_inputs(self, target, sources, K):
-        from .stn import inverse_intrinsics
         if self.static is None:
             self.static = {"target": target.clone(), "sources": [s.clone() for s in sources], "K": K.clone()}
             self.static["imgs"] = torch.cat([self.static["target"]] + self.static["sources"], 0)
             bsz = target.shape[0]
             with torch.no_grad():
                 self.static["init_disp"] = self.depth_net(self.static["imgs"])[0][0:bsz].clone()
-            self.kinv = inverse_intrinsics(self.static["K"])      # the buffer the captured graphs read
             return
         s = self.static
         with torch.no_grad():
@@ -159,7 +157,6 @@ class WindowRunner:
                 dst.copy_(src)
             s["imgs"].copy_(torch.cat([s["target"]] + s["sources"], 0))
             s["K"].copy_(K)
-            self.kinv.copy_(K.inverse())
             s["init_disp"].copy_(self.depth_net(s["imgs"])[0][0:target.shape[0]])
 
     def __call__(self, target_img, source_imgs, intrinsics):

@@ -76,21 +76,13 @@ def pose_vec2mat(vec, rotation_mode='euler'):
     return torch.cat([rot_mat, translation], dim=2)
 
 
-_KINV_CACHE = {}
-
-
 def inverse_intrinsics(intrinsics):
-    """`intrinsics.inverse()` (models/stn.py:257), memoised per tensor version: K is a loader
-    output that stays constant across the warps/losses of a step, and the batched LU costs
-    half a dozen launches (and cannot be captured into a CUDA graph)."""
-    key = (intrinsics.data_ptr(), intrinsics._version, intrinsics.device, tuple(intrinsics.shape))
-    hit = _KINV_CACHE.get(key)
-    if hit is None:
-        if len(_KINV_CACHE) > 64:
-            _KINV_CACHE.clear()
-        hit = (intrinsics.detach().inverse(), intrinsics)      # keeps K alive so the pointer stays unique
-        _KINV_CACHE[key] = hit
-    return hit[0]
+    """`intrinsics.inverse()` (models/stn.py:257) with the reference's bits (the same batched LU),
+    recomputed on every call like the reference does.  `inv_ex` skips the device -> host error
+    check of `.inverse()`, so the call neither synchronises nor breaks CUDA-graph capture; callers
+    that warp several times with one K (Compute_Loss.forward, solve_pose_iteratively) compute it
+    once per call and pass it down."""
+    return torch.linalg.inv_ex(intrinsics.detach())[0]
 
 
 def projection_matrices(pose, intrinsics, kinv=None):
