@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 7
+#define TCSFM_ABI_VERSION 8
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -94,6 +94,12 @@ int tcsfm_ssim_fwd(const float* x, const float* y, float* out,
                    int N, int H, int W, int flags, void* stream);
 int tcsfm_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y,
                    int N, int H, int W, int flags, void* stream);
+/* SSIM_Loss(x, y).mean() as one launch each way (the depth-initialisation term of the PFT loss,
+ * optimization_experiments/optimizer.py:89-90): out_mean[1] is zeroed and accumulated; g_mean[1] is the
+ * device scalar upstream of the mean. */
+int tcsfm_ssim_mean_fwd(const float* x, const float* y, float* out_mean, int N, int H, int W, int flags, void* stream);
+int tcsfm_ssim_mean_bwd(const float* x, const float* y, const float* g_mean, float* g_x, float* g_y,
+                        int N, int H, int W, int flags, void* stream);
 
 /* ---- Compute_Loss.compute_pairwise_loss (losses.py:151-183) fused with
  *      mean_on_mask's sums (losses.py:142-149) --------------------------------------
@@ -147,11 +153,42 @@ int tcsfm_photo_coef_planes(void);
 int tcsfm_photo_fwd(const float* tgt, int64_t tgt_sb, int64_t tgt_sc, const float* src, int64_t src_sb, int64_t src_sc,
                     const float* rec, const float* proj_depth, const float* comp_depth,
                     float* auto_err, float* diff, float* auto_mask, float* weight, float* coef,
+                    const float* valid,
                     int N, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
+/* `valid` [N,1,H,W] (may be NULL): inverse_warp2's valid_mask; when given auto_mask comes out already
+ * multiplied by it (helpers.py:18 returns auto_mask * valid_mask). */
 int tcsfm_photo_bwd(const float* tgt, int64_t tgt_sb, int64_t tgt_sc, const float* rec,
                     const float* proj_depth, const float* comp_depth, const float* coef,
                     const float* g_diff, const float* g_weight, float* g_rec, float* g_pd, float* g_cd,
                     int N, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
+
+/* ---- DepthOptimizer.compute_optimization_loss (optimization_experiments/optimizer.py:45-86): the
+ *      reduction of the error maps of solve_pose_iteratively(return_errors=True) to the PFT loss --------
+ * The maps are the two halves of the stacked [2*S*B,1,H,W] outputs (train_mono.py:94-100): forward half
+ * (target <- source j: rows j*B .. j*B+B-1) f_diff, f_valid, f_aerr (auto_mask_error), f_weight; inverse half
+ * i_diff, i_valid, i_auto (auto_mask), i_weight; n = H*W.
+ *   TCSFM_PFT_ARGMIN       options['diff_img_argmin']: per-pixel min over the S sources (first index on ties),
+ *                          valid = clamp(sum_j valid_j, 0, 1) [* (min diff < min auto_err) with AUTOMASK],
+ *                          sum(diff_min * valid * f_weight[0:B]) / sum(valid)          (optimizer.py:49-69);
+ *                          without it 0.25 * sum(f_diff * f_valid * f_weight) / sum(f_valid)       (:71-73)
+ *   TCSFM_PFT_AUTOMASK     options['automasking']
+ *   TCSFM_PFT_INVERSE      options['l_inverse_reconstruction']: + 0.25 * sum(i_diff * i_valid * i_weight [* i_auto])
+ *                          / sum(i_valid [* i_auto])                                                (:75-81)
+ *   TCSFM_PFT_DEPTH_CONSIST options['l_depth_consist']: + w_depth * mean(1 - f_weight) [+ w_depth * mean(1 - i_weight)]
+ * sums [8] workspace (zeroed by the forward, read by the backward); loss [1].  The backward writes the
+ * gradients w.r.t. diff_img and weight_mask of both halves (every element, no accumulation); the masks and
+ * auto_mask_error are comparisons and carry none. */
+#define TCSFM_PFT_ARGMIN         (1 << 0)
+#define TCSFM_PFT_AUTOMASK       (1 << 1)
+#define TCSFM_PFT_INVERSE        (1 << 2)
+#define TCSFM_PFT_DEPTH_CONSIST  (1 << 3)
+int tcsfm_pft_reduce_fwd(const float* f_diff, const float* f_valid, const float* f_aerr, const float* f_weight,
+                         const float* i_diff, const float* i_valid, const float* i_auto, const float* i_weight,
+                         int B, int S, int64_t n, int flags, float w_depth, float* sums, float* loss, void* stream);
+int tcsfm_pft_reduce_bwd(const float* f_diff, const float* f_valid, const float* f_aerr, const float* f_weight,
+                         const float* i_diff, const float* i_valid, const float* i_auto, const float* i_weight,
+                         int B, int S, int64_t n, int flags, float w_depth, const float* sums, const float* g_loss,
+                         float* g_f_diff, float* g_f_weight, float* g_i_diff, float* g_i_weight, void* stream);
 
 /* ---- get_smooth_loss (losses.py:43-61): edge-aware smoothness of the mean-normalised disparity --
  * disp [B,1,H,W] contiguous, img [B,3,H,W] view; workspace: 2*B+2 floats kept between forward and

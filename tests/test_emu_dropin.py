@@ -461,3 +461,73 @@ def test_intrinsics_inverse_is_never_stale():
     assert torch.equal(stn.inverse_intrinsics(k.transpose(1, 2)), k.transpose(1, 2).inverse())
     k.data[:, 0, 0] = 500.0
     assert torch.equal(stn.inverse_intrinsics(k), k.inverse())
+
+
+PFT_VARIANTS = [
+    {},                                                     # the scripts' defaults (run_sequential_optimization.py:69-99)
+    {"diff_img_argmin": False},
+    {"automasking": False},
+    {"l_inverse_reconstruction": False},
+    {"l_depth_consist": False},
+    {"diff_img_argmin": False, "automasking": False, "l_depth_consist": False},
+    {"l_depth_init": False, "l_smooth": True, "l_pose_consist": True},
+]
+
+
+@pytest.mark.parametrize("n_src", [1, 2, 3])
+@pytest.mark.parametrize("variant", range(len(PFT_VARIANTS)))
+def test_pft_reduce_option_matrix_vs_oracle(emu_ops, n_src, variant):
+    """tcsfm_pft_reduce_fwd/bwd against the oracle's restatement of optimizer.py:45-97 for every option
+    switch, 1-3 sources, maps handed over as slices of one stack (the zero-copy path) and as separate
+    tensors (the concatenating path), with ties in the per-pixel minimum."""
+    from oracle import ref_torch as O
+    from tcsfm_b200 import pft
+    opts = dict(goldens.PFT_OPTIONS, num_source_imgs=n_src, **PFT_VARIANTS[variant])
+    gen = torch.Generator().manual_seed(100 * n_src + variant)
+    bsz, h, w = 2, 9, 13
+    rows = 2 * n_src * bsz
+    diff = torch.rand(rows, 1, h, w, generator=gen)
+    diff[bsz:2 * bsz] = torch.where(torch.rand(bsz, 1, h, w, generator=gen) < 0.3, diff[0:bsz], diff[bsz:2 * bsz])  # ties
+    valid = (torch.rand(rows, 1, h, w, generator=gen) < 0.8).float()
+    aerr = torch.rand(rows, 1, h, w, generator=gen)
+    amask = (torch.rand(rows, 1, h, w, generator=gen) < 0.7).float()
+    weight = torch.rand(rows, 1, h, w, generator=gen)
+    target = torch.rand(bsz, 3, h, w, generator=gen)
+    disp0 = torch.rand(bsz, 1, h, w, generator=gen)
+    poses = torch.randn(rows, 3, 6, generator=gen) * 0.01
+    split = n_src * bsz
+    results = []
+    for mode in ("stacked", "separate", "oracle"):
+        d, wt, td = leaf(diff), leaf(weight), leaf(disp0)
+        if mode == "separate":
+            halves = lambda t: (t[:split].clone(), t[split:].clone())   # noqa: E731
+        else:
+            halves = lambda t: (t[:split], t[split:])                   # noqa: E731
+        data = [{}, {}]
+        for key, t in (("diff_img", d), ("valid_mask", valid), ("auto_mask_error", aerr), ("auto_mask", amask),
+                       ("weight_mask", wt), ("poses", poses)):
+            data[0][key], data[1][key] = halves(t)
+        fn = O.pft_window_loss if mode == "oracle" else pft.compute_optimization_loss
+        loss = fn(opts, target, td, disp0 * 0.9 + 0.02, data[0], data[1])
+        loss.sum().backward()
+        results.append((float(loss.detach()), d.grad, wt.grad, td.grad, loss.shape))
+    ref = results[2]
+    for got in results[:2]:
+        assert got[4] == ref[4]                                  # [1] with the arg-min term, 0-d without
+        assert abs(got[0] - ref[0]) <= 2e-6 * abs(ref[0]), (got[0], ref[0])
+        assert rel_l2(got[1], ref[1]) < 1e-5
+        if ref[2] is not None and float(ref[2].abs().sum()) > 0:
+            assert rel_l2(got[2], ref[2]) < 1e-5
+        if ref[3] is not None:
+            assert rel_l2(got[3], ref[3]) < 5e-4
+
+
+def test_ssim_mean_matches_map_mean(emu_ops):
+    x, y = torch.rand(2, 1, 19, 70), torch.rand(2, 1, 19, 70)
+    xa, xb = leaf(x), leaf(x)
+    a = ops.SsimMeanFn.apply(xa, y)
+    b = losses.SSIM_Loss()(xb, y).mean()
+    assert abs(float(a) - float(b)) < 1e-6 * abs(float(b))
+    (3.0 * a).sum().backward()
+    (3.0 * b).backward()
+    assert rel_l2(xa.grad, xb.grad) < 1e-5

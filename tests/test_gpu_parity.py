@@ -508,3 +508,187 @@ def test_randomised_sweep_vs_eager_cuda(seed):
     pr = O.pairwise_loss(cfg, *args)
     pg = losses.Compute_Loss(cfg).compute_pairwise_loss(*args, 5)
     assert torch.equal(pg[3], pr[3]) and torch.equal(pg[2], pr[2]), (seed, int((pg[3] != pr[3]).sum()))
+
+
+# ------------------------------------------------- PFT block (train_mono.py:84-92, optimizer.py:45-97, helpers.py:8-23)
+def _pft_stack(b, h, w, rng, seed, n_src=2):
+    """The stacked tensors solve_pose_iteratively builds (train_mono.py:54-67) and one warp of them."""
+    fr = frames(b, h, w, 0.02, rng, seed=seed) if n_src == 2 else \
+        synth.make_frames(b, h, w, n_src=n_src, seed=seed, yaw=0.02, depth_range=rng, device=DEV,
+                          intrinsics=synth.scaled_intrinsics(h, w))
+    tgt = fr["target"].repeat(n_src, 1, 1, 1)
+    src = torch.cat(fr["sources"], 0)
+    imgs = torch.cat([torch.cat([tgt, src], 1), torch.cat([src, tgt], 1)], 0)
+    td = fr["depths"][0].repeat(n_src, 1, 1, 1)
+    sd = torch.cat(fr["depths"][1:], 0)
+    depth, ref_depth = torch.cat([td, sd], 0), torch.cat([sd, td], 0)
+    poses = torch.cat(list(fr["poses"]) + list(fr["poses_inv"]), 0)
+    K = fr["K"].repeat(2 * n_src, 1, 1)
+    with torch.no_grad():
+        rec, valid, pd, cd = O.inverse_warp2(imgs[:, 3:6], depth, ref_depth, -poses, K, 'zeros')
+    return fr, imgs, rec, valid, pd, cd
+
+
+@pytest.mark.parametrize("shape", [(6, 192, 640, synth.KITTI_DEPTH_RANGE), (16, 256, 320, synth.SCANNET_DEPTH_RANGE),
+                                   (2, 50, 77, synth.KITTI_DEPTH_RANGE)])
+def test_photo_error_maps_bit_exact_vs_eager_cuda(shape):
+    """tcsfm_photo_fwd: auto_mask_error, diff_img, auto_mask, weight_mask of train_mono.py:84-92 at the stacked
+    batch 2*S*B (24 at 192x640, 32 at 256x320), bit for bit against eager PyTorch on the same GPU; tcsfm_photo_bwd:
+    gradients w.r.t. the reconstruction and the two depths within 1e-4."""
+    from tcsfm_b200 import train_mono
+    b, h, w, rng = shape
+    n_src = 2 if h != 256 else 1
+    _, imgs, rec, _, pd, cd = _pft_stack(b, h, w, rng, seed=31, n_src=n_src)
+    up_d, up_w = torch.rand_like(pd), torch.randn_like(pd)
+    res = []
+    for fn in (O.pft_error_maps, train_mono.photometric_error_maps):
+        r, p, c = leaf(rec), leaf(pd), leaf(cd)
+        aerr, diff, amask, weight = fn(imgs, r, p, c)
+        ((diff * up_d).sum() + (weight * up_w).sum()).backward()
+        res.append((aerr, diff, amask, weight, r.grad, p.grad, c.grad))
+    ref, got = res
+    for name, a, b_ in zip(("auto_mask_error", "diff_img", "auto_mask", "weight_mask"), got[:4], ref[:4]):
+        assert torch.equal(a.reshape(b_.shape), b_), (name, int((a.reshape(b_.shape) != b_).sum()))
+    assert not got[2].requires_grad
+    for name, a, b_ in zip(("g_rec", "g_proj_depth", "g_comp_depth"), got[4:], ref[4:]):
+        assert rel_l2(a, b_) < 1e-4, (name, rel_l2(a, b_))
+
+
+@pytest.mark.parametrize("shape", [(6, 192, 640, synth.KITTI_DEPTH_RANGE, 2), (16, 256, 320, synth.SCANNET_DEPTH_RANGE, 1),
+                                   (3, 96, 160, synth.KITTI_DEPTH_RANGE, 3)])
+@pytest.mark.parametrize("variant", [{}, {"diff_img_argmin": False}, {"automasking": False, "l_depth_consist": False},
+                                     {"l_inverse_reconstruction": False}])
+def test_compute_optimization_loss_vs_eager_cuda(shape, variant):
+    """solve_pose_iteratively(return_errors=True) + compute_optimization_loss (optimizer.py:45-97) through the
+    fused kernels (warp + stack, photometric maps, tcsfm_pft_reduce, SSIM mean) against the oracle on the same
+    GPU: PFT auto-mask / valid masks bit-exact, loss within 1e-5, gradients w.r.t. the depths within 1e-4."""
+    from tcsfm_b200 import pft, train_mono
+    b, h, w, rng, n_src = shape
+    fr = synth.make_frames(b, h, w, n_src=n_src, seed=17, yaw=0.01, depth_range=rng, device=DEV,
+                           intrinsics=synth.scaled_intrinsics(h, w))
+    net = synth.TinyPoseNet(seed=5).to(DEV)
+    opts = dict(goldens.PFT_OPTIONS, num_source_imgs=n_src, **variant)
+    res = []
+    for impl in ("oracle", "cuda"):
+        dl = [leaf(d) for d in fr["depths"]]
+        tdisp = leaf(fr["disps"][0])
+        if impl == "oracle":
+            poses, poses_inv, out = O.iterative_pose(3, dl, net, fr["target"], fr["sources"], fr["K"], return_errors=True)
+            loss = O.pft_window_loss(opts, fr["target"], tdisp, fr["disps"][0] * 0.9 + 0.02, out["fwd"], out["inv"])
+        else:
+            poses, poses_inv, out = train_mono.solve_pose_iteratively(3, dl, net, fr["target"], fr["sources"], fr["K"],
+                                                                      return_errors=True)
+            loss = pft.compute_optimization_loss(opts, fr["target"], tdisp, fr["disps"][0] * 0.9 + 0.02,
+                                                 out["fwd"], out["inv"])
+        loss.sum().backward()
+        res.append((loss.detach(), out, [d.grad for d in dl], tdisp.grad, poses, poses_inv))
+    ref, got = res
+    for side in ("fwd", "inv"):
+        for k in ("valid_mask", "auto_mask"):
+            assert torch.equal(got[1][side][k], ref[1][side][k]), (side, k)
+        for k in ("diff_img", "weight_mask", "auto_mask_error", "img_rec"):
+            assert torch.equal(got[1][side][k], ref[1][side][k]), (side, k)
+    assert got[0].shape == ref[0].shape
+    assert abs(float(got[0]) - float(ref[0])) <= 1e-5 * abs(float(ref[0])), (float(got[0]), float(ref[0]))
+    for j in range(1 + n_src):
+        assert rel_l2(got[2][j], ref[2][j]) < 1e-4, (j, rel_l2(got[2][j], ref[2][j]))
+    # the depth-init term is SSIM on two smooth, 0.9-correlated maps: the reference's own fp32 gradient is
+    # ~6e-4 from its fp64 evaluation there (test_ssim_gradient_noise_floor_on_gpu)
+    assert rel_l2(got[3], ref[3]) < 5e-4
+    for a, b_ in zip(got[4] + got[5], ref[4] + ref[5]):
+        assert torch.equal(a, b_)
+
+
+@pytest.mark.parametrize("hw", [(192, 640), (256, 320), (50, 77)])
+def test_compute_photometric_error_vs_eager_cuda(hw):
+    """helpers.py:8-23 at batch 1 (the loss-surface sweeps): every returned map bit for bit."""
+    from tcsfm_b200 import pft
+    h, w = hw
+    fr = frames(1, h, w, 0.02, synth.KITTI_DEPTH_RANGE, seed=23)
+    args = (fr["target"], fr["sources"][0], fr["depths"][0], fr["depths"][1], fr["poses"][0], fr["K"])
+    with torch.no_grad():
+        ref, got = O.photometric_error(*args), pft.compute_photometric_error(*args)
+    for k in ("diff_img", "img_rec", "valid_mask", "weight_mask"):
+        assert torch.equal(got[k], ref[k]), (k, int((got[k] != ref[k]).sum()))
+
+
+@pytest.mark.parametrize("shape", [(8, 3, 192, 640), (4, 1, 256, 320), (2, 3, 51, 67)])
+def test_ssim_vs_eager_cuda(shape):
+    """Standalone SSIM_Loss with the CUDA arithmetic flavour against eager PyTorch on the same device: the map bit
+    for bit, gradients w.r.t. both arguments within 1e-4 on textured inputs."""
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.rand(shape, device=DEV, generator=gen)
+    y = (x + 0.1 * torch.randn(shape, device=DEV, generator=gen)).clamp(0, 1)
+    up = torch.randn(shape, device=DEV, generator=gen)
+    res = []
+    for fn in (O.ssim_dissimilarity, losses.SSIM_Loss()):
+        xx, yy = leaf(x), leaf(y)
+        out = fn(xx, yy)
+        (out * up).sum().backward()
+        res.append((out, xx.grad, yy.grad))
+    ref, got = res
+    assert torch.equal(got[0], ref[0]), int((got[0] != ref[0]).sum())
+    assert rel_l2(got[1], ref[1]) < 1e-4 and rel_l2(got[2], ref[2]) < 1e-4
+    mean = ops.SsimMeanFn.apply(x, y)
+    assert abs(float(mean) - float(ref[0].mean())) <= 1e-6 * float(ref[0].mean())
+
+
+def test_ssim_gradient_noise_floor_on_gpu():
+    """On smooth, highly correlated inputs (the disparity-init term, optimizer.py:89-90) the kernel's gradient is
+    closer to the reference's fp32 autograd than that is to its own fp64 evaluation (the documented exception
+    to the 1e-4 gradient tolerance)."""
+    g = Golden("mid_b2_64x96", DEV)
+    x = g.frames()["disps"][0]
+    y = x * 0.9 + 0.02
+    gout = torch.full_like(x, 0.1 / x.numel())
+
+    def ref(dtype):
+        xx = x.to(dtype).clone().requires_grad_(True)
+        (O.ssim_dissimilarity(xx, y.to(dtype)) * gout.to(dtype)).sum().backward()
+        return xx.grad
+    r32, r64 = ref(torch.float32), ref(torch.float64)
+    xx = leaf(x)
+    (losses.SSIM_Loss()(xx, y) * gout).sum().backward()
+    assert rel_l2(xx.grad, r32) < rel_l2(r32, r64)
+    assert rel_l2(xx.grad, r64) < 1.5 * rel_l2(r32, r64)
+
+
+def test_graph_replay_follows_changed_intrinsics():
+    """K^-1 is recomputed inside every call (models/stn.py:257), so a captured step replayed after the static K
+    buffer was overwritten gives the eager result for the new K (round-1 finding: a memoised K^-1 was baked in)."""
+    b, h, w = 2, 96, 160
+    fr = frames(b, h, w, 0.01, synth.KITTI_DEPTH_RANGE, seed=3)
+    mod = losses.Compute_Loss(goldens.FULL_CFG)
+    K = fr["K"].clone()
+    disps = [leaf(d) for d in fr["disps"]]
+    poses, poses_inv = [leaf(p) for p in fr["poses"]], [leaf(p) for p in fr["poses_inv"]]
+
+    def step():
+        for t in disps:
+            t.grad = None
+        out = mod(fr["sources"], fr["target"], [poses, poses_inv], [[d] for d in disps], K)
+        out["total"].backward()
+        return out["total"]
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_total = step()
+    K2 = fr["K"].clone()
+    K2[:, 0, 0] *= 1.07
+    K2[:, 1, 2] += 3.0
+    K.copy_(K2)
+    graph.replay()
+    got, got_grad = static_total.detach().clone(), disps[0].grad.clone()
+    ref = step()
+    assert torch.equal(got, ref.detach())
+    assert rel_l2(got_grad, disps[0].grad) < 1e-6
+    fresh = [leaf(d) for d in fr["disps"]]
+    out = O.compute_loss(goldens.FULL_CFG, fr["sources"], fr["target"], [fr["poses"], fr["poses_inv"]],
+                         [[d] for d in fresh], K2)
+    assert abs(float(got) - float(out["total"])) <= 1e-5 * abs(float(out["total"]))

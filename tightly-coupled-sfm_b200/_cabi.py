@@ -2,7 +2,7 @@
 package loader and by the test-only emulator binding)."""
 import ctypes as C
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 ARITH_CPU = 1 << 0
 AUTO_MASK = 1 << 1
@@ -11,6 +11,11 @@ DEPTH_MASK = 1 << 3
 DEPTH_CONSIST = 1 << 4
 SHARED_GRADS = 1 << 5
 ARITH_BMM_NOFMA = 1 << 6
+
+PFT_ARGMIN = 1 << 0
+PFT_AUTOMASK = 1 << 1
+PFT_INVERSE = 1 << 2
+PFT_DEPTH_CONSIST = 1 << 3
 
 _fp = C.c_void_p          # device (or, in the emulator, host) pointer to float
 _i64 = C.c_int64
@@ -44,13 +49,18 @@ SIGNATURES = {
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tcsfm_ssim_fwd": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tcsfm_ssim_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tcsfm_ssim_mean_fwd": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tcsfm_ssim_mean_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tcsfm_pft_reduce_fwd": (C.c_int, [_fp] * 8 + [C.c_int, C.c_int, _i64, C.c_int, C.c_float, _fp, _fp, C.c_void_p]),
+    "tcsfm_pft_reduce_bwd": (C.c_int, [_fp] * 8 + [C.c_int, C.c_int, _i64, C.c_int, C.c_float, _fp, _fp,
+                                                    _fp, _fp, _fp, _fp, C.c_void_p]),
     "tcsfm_pair_coef_planes": (C.c_int, []),
     "tcsfm_pair_loss_fwd": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "tcsfm_pair_loss_bwd": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "tcsfm_photo_coef_planes": (C.c_int, []),
-    "tcsfm_photo_fwd": (C.c_int, [_fp, _i64, _i64, _fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
+    "tcsfm_photo_fwd": (C.c_int, [_fp, _i64, _i64, _fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                                   C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "tcsfm_photo_bwd": (C.c_int, [_fp, _i64, _i64, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                                   C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),

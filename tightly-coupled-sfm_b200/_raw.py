@@ -142,6 +142,32 @@ def ssim_bwd(lib, x, y, g_out, need_x=True, need_y=True, flags=0):
     return g_x, g_y
 
 
+def ssim_mean_fwd(lib, x, y, flags=0):
+    """mean(SSIM_Loss(x, y)) as a [1] tensor, one launch (no map is written)."""
+    x, y = _f32c(x, "x"), _f32c(y, "y")
+    if x.shape != y.shape or x.dim() != 4:
+        raise ValueError("ssim: x and y must be [B,C,H,W] of equal shape")
+    b, c, h, w = x.shape
+    out = torch.empty((1,), dtype=torch.float32, device=x.device)
+    with _timing.launch("ssim_mean_fwd", x.is_cuda):
+        rc = lib.tcsfm_ssim_mean_fwd(_ptr(x), _ptr(y), _ptr(out), b * c, h, w, flags, _stream(x))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return out
+
+
+def ssim_mean_bwd(lib, x, y, g_mean, need_x=True, need_y=True, flags=0):
+    x, y, g_mean = _f32c(x, "x"), _f32c(y, "y"), _f32c(g_mean, "g_mean")
+    b, c, h, w = x.shape
+    g_x = torch.empty_like(x) if need_x else None
+    g_y = torch.empty_like(x) if need_y else None
+    with _timing.launch("ssim_mean_bwd", x.is_cuda):
+        rc = lib.tcsfm_ssim_mean_bwd(_ptr(x), _ptr(y), _ptr(g_mean), _ptr(g_x), _ptr(g_y), b * c, h, w, flags, _stream(x))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return g_x, g_y
+
+
 class PairBatch:
     """Host-side descriptor array for one multi-group pair-loss launch; keeps every
     tensor it points at alive."""
@@ -323,8 +349,12 @@ def pair_loss_bwd_shared(lib, batch, mask, sums, coef, g_scalars, g_min, min_inf
 # photometric error maps of solve_pose_iteratively(return_errors=True) (csrc/photo_kernels.cu)
 # ---------------------------------------------------------------------------
 
-def photo_fwd(lib, tgt, src, rec, proj_depth, comp_depth, w_l1, w_ssim, flags=0, want_grad=True):
+def photo_fwd(lib, tgt, src, rec, proj_depth, comp_depth, w_l1, w_ssim, flags=0, want_grad=True, valid=None):
+    """valid: optional inverse_warp2 valid_mask [N,1,H,W]; when given the returned auto_mask is already
+    multiplied by it (helpers.py:18)."""
     n, _, h, w = rec.shape
+    _expect(valid, (n, 1, h, w), "valid")
+    valid = _f32c(valid, "valid")
     for t, name in ((tgt, "tgt"), (src, "src"), (rec, "rec")):
         _expect(t, (n, 3, h, w), name)
     _expect(proj_depth, (n, 1, h, w), "proj_depth")
@@ -337,7 +367,7 @@ def photo_fwd(lib, tgt, src, rec, proj_depth, comp_depth, w_l1, w_ssim, flags=0,
     coef = torch.empty((n, lib.tcsfm_photo_coef_planes(), h, w), dtype=torch.float32, device=dev) if want_grad else None
     with _timing.launch("photo_fwd", rec.is_cuda):
         rc = lib.tcsfm_photo_fwd(_ptr(tgt), tsb, tsc, _ptr(src), ssb, ssc, _ptr(rec), _ptr(pd), _ptr(cd),
-                                 _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), _ptr(coef),
+                                 _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]), _ptr(coef), _ptr(valid),
                                  n, h, w, w_l1, w_ssim, flags, _stream(rec))
     _cabi.check(lib, rc)
     _timing.count_launch()
@@ -438,3 +468,54 @@ def smooth_bwd(lib, disp, img, ws, g_out):
     _cabi.check(lib, rc)
     _timing.count_launch(2)
     return g_disp
+
+
+# ---------------------------------------------------------------------------
+# PFT loss reduction (csrc/pft_kernels.cu; optimization_experiments/optimizer.py:45-86)
+# ---------------------------------------------------------------------------
+
+def _halves(t, split, name):
+    """(forward half, inverse half) pointers of a stacked [2*S*B,1,H,W] map."""
+    t = _f32c(t, name)
+    return t, t.data_ptr(), t.data_ptr() + split * t[0].numel() * 4
+
+
+def pft_reduce_fwd(lib, diff, valid, auto_err, auto_mask, weight, bsz, n_src, flags, w_depth):
+    """The maps are the stacked [2*S*B,1,H,W] outputs of solve_pose_iteratively(return_errors=True)
+    (forward half first).  Returns (loss [1], sums [8])."""
+    split = bsz * n_src
+    n = diff[0].numel()
+    for t, name in ((diff, "diff_img"), (valid, "valid_mask"), (auto_err, "auto_mask_error"), (auto_mask, "auto_mask"),
+                    (weight, "weight_mask")):
+        _expect(t, (2 * split,) + tuple(diff.shape[1:]), name)
+    keep = [_halves(t, split, name) for t, name in ((diff, "diff"), (valid, "valid"), (auto_err, "auto_err"),
+                                                     (auto_mask, "auto_mask"), (weight, "weight"))]
+    (_, d_f, d_i), (_, v_f, v_i), (_, a_f, _), (_, _, m_i), (_, w_f, w_i) = keep
+    dev = diff.device
+    sums = torch.empty((8,), dtype=torch.float32, device=dev)
+    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    with _timing.launch("pft_reduce_fwd", diff.is_cuda):
+        rc = lib.tcsfm_pft_reduce_fwd(d_f, v_f, a_f, w_f, d_i, v_i, m_i, w_i, bsz, n_src, n, flags, w_depth,
+                                      _ptr(sums), _ptr(loss), _stream(diff))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return loss, sums, [k[0] for k in keep]
+
+
+def pft_reduce_bwd(lib, maps, sums, g_loss, bsz, n_src, flags, w_depth):
+    """maps: the contiguous tensors the forward used.  Returns (g_diff, g_weight), each [2*S*B,1,H,W]."""
+    diff, valid, auto_err, auto_mask, weight = maps
+    split = bsz * n_src
+    n = diff[0].numel()
+    half = split * n * 4
+    g_loss = _f32c(g_loss, "g_loss")
+    g_diff, g_weight = torch.empty_like(diff), torch.empty_like(weight)
+    with _timing.launch("pft_reduce_bwd", diff.is_cuda):
+        rc = lib.tcsfm_pft_reduce_bwd(diff.data_ptr(), valid.data_ptr(), auto_err.data_ptr(), weight.data_ptr(),
+                                      diff.data_ptr() + half, valid.data_ptr() + half, auto_mask.data_ptr() + half,
+                                      weight.data_ptr() + half, bsz, n_src, n, flags, w_depth, _ptr(sums), _ptr(g_loss),
+                                      g_diff.data_ptr(), g_weight.data_ptr(), g_diff.data_ptr() + half,
+                                      g_weight.data_ptr() + half, _stream(diff))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return g_diff, g_weight

@@ -21,6 +21,7 @@ struct PhotoArgs {
     const float* src; int64_t src_sb, src_sc;
     const float* rec;                 // [N,3,H,W] contiguous
     const float* pd; const float* cd; // [N,1,H,W]
+    const float* valid;               // [N,1,H,W] or NULL: folded into auto_mask (helpers.py:18)
     float* auto_err; float* diff; float* auto_mask; float* weight;
     float* coef;                      // [N,9,H,W] workspace (fwd writes, bwd reads) or NULL
     const float* g_diff; const float* g_weight;
@@ -113,7 +114,7 @@ photo_fwd_kernel(const __grid_constant__ PhotoArgs P) {
             const float aerr = mean3_of_sum<F>(e_src[k], A);
             if (P.diff) P.diff[o] = diff;
             if (P.auto_err) P.auto_err[o] = aerr;
-            if (P.auto_mask) P.auto_mask[o] = (diff < aerr) ? 1.f : 0.f;
+            if (P.auto_mask) P.auto_mask[o] = (diff < aerr) ? (P.valid ? __ldg(P.valid + o) : 1.f) : 0.f;
             if (P.weight) P.weight[o] = __fsub_rn(1.0f, depth_inconsistency(__ldg(P.cd + o), __ldg(P.pd + o)));
         }
     }
@@ -220,12 +221,13 @@ extern "C" int tcsfm_photo_coef_planes(void) { return kPhotoCoefPlanes; }
 extern "C" int tcsfm_photo_fwd(const float* tgt, int64_t tgt_sb, int64_t tgt_sc, const float* src, int64_t src_sb, int64_t src_sc,
                                const float* rec, const float* proj_depth, const float* comp_depth,
                                float* auto_err, float* diff, float* auto_mask, float* weight, float* coef,
+                               const float* valid,
                                int N, int H, int W, float w_l1, float w_ssim, int flags, void* stream) {
     PhotoArgs P;
     memset(&P, 0, sizeof(P));
     P.tgt = tgt; P.tgt_sb = tgt_sb; P.tgt_sc = tgt_sc; P.src = src; P.src_sb = src_sb; P.src_sc = src_sc;
     P.rec = rec; P.pd = proj_depth; P.cd = comp_depth;
-    P.auto_err = auto_err; P.diff = diff; P.auto_mask = auto_mask; P.weight = weight; P.coef = coef;
+    P.auto_err = auto_err; P.diff = diff; P.auto_mask = auto_mask; P.weight = weight; P.coef = coef; P.valid = valid;
     if (int rc = fill_photo(P, N, H, W, w_l1, w_ssim, flags, "tcsfm_photo_fwd")) return rc;
     if (!src) { set_error("tcsfm_photo_fwd: null src"); return 1; }
     const size_t smem = 6 * Tile<1>::kCells * sizeof(float2);

@@ -11,11 +11,15 @@ namespace tcsfm {
 static const float kC1 = (float)(0.01 * 0.01);
 static const float kC2 = (float)(0.03 * 0.03);
 
+// kMean: instead of the map, accumulate mean(map) into out[0] (`scale` = 1 / element count): the
+// `.mean()` that follows SSIM_Loss in the PFT depth-initialisation term (optimizer.py:89-90)
+template <bool kMean>
 __global__ void __launch_bounds__(kTileThreads)
 ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
-                int H, int W, float C1, float C2) {
+                int H, int W, float C1, float C2, float scale) {
     using T1 = Tile<1>;
     TCSFM_DYN_SMEM(float, smem);
+    TCSFM_SHARED float red[kTileThreads / 32];
     float* xs = smem;
     float* ys = smem + T1::kCells;
     const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
@@ -27,6 +31,7 @@ ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float*
         ys[cell] = ok ? __ldg(y + plane + (int64_t)ry * W + rx) : 0.f;
     }
     __syncthreads();
+    float part[1] = {0.f};
 #pragma unroll
     for (int k = 0; k < kPixPerThread; ++k) {
         int tx, ty;
@@ -34,13 +39,17 @@ ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float*
         const int gx = x0 + tx, gy = y0 + ty;
         if (gx < W && gy < H) {
             const int c = T1::cell(tx, ty);
-            out[plane + (int64_t)gy * W + gx] = ssim_value(xs + c, ys + c, T1::kPitch, C1, C2);
+            const float v = ssim_value(xs + c, ys + c, T1::kPitch, C1, C2);
+            if (kMean) part[0] += v * scale;
+            else out[plane + (int64_t)gy * W + gx] = v;
         }
     }
+    if (kMean) block_atomic_accumulate<1>(part, red, out, threadIdx.x, kTileThreads);
 }
 
 __global__ void __launch_bounds__(kTileThreads)
 ssim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g_out,
+                const float* __restrict__ g_mean, float scale,
                 float* __restrict__ g_x, float* __restrict__ g_y, int H, int W, float C1, float C2) {
     using T2 = Tile<2>;
     using T1 = Tile<1>;
@@ -68,7 +77,8 @@ ssim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
         SsimCoef k;
         k.Ax = k.Ay = k.B = k.Cc = 0.f;
         if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
-            const float g = __ldg(g_out + plane + (int64_t)gy * W + gx);
+            // upstream: a per-pixel map, or the gradient of the map's mean (one device scalar / count)
+            const float g = g_out ? __ldg(g_out + plane + (int64_t)gy * W + gx) : __ldg(g_mean) * scale;
             const int c2 = T2::cell(cx, cy);
             const SsimStats s = ssim_stats(xs + c2, ys + c2, T2::kPitch);
             k = ssim_coef(s, ssim_terms(s, C1, C2), g);
@@ -113,8 +123,21 @@ extern "C" int tcsfm_ssim_fwd(const float* x, const float* y, float* out, int N,
     if (N > 65535) { set_error("tcsfm_ssim_fwd: N=%d exceeds 65535 planes", N); return 1; }
     dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, N), block(kTileThreads);
     const size_t smem = 2 * Tile<1>::kCells * sizeof(float);
-    TCSFM_LAUNCH(ssim_fwd_kernel, grid, block, smem, stream, x, y, out, H, W, kC1, kC2);
+    TCSFM_LAUNCH(ssim_fwd_kernel<false>, grid, block, smem, stream, x, y, out, H, W, kC1, kC2, 0.f);
     return check_launch("tcsfm_ssim_fwd");
+}
+
+extern "C" int tcsfm_ssim_mean_fwd(const float* x, const float* y, float* out_mean, int N, int H, int W, int flags, void* stream) {
+    (void)flags;
+    if (N <= 0 || H < 2 || W < 2) { set_error("tcsfm_ssim_mean_fwd: bad shape N=%d H=%d W=%d", N, H, W); return 1; }
+    if (!x || !y || !out_mean) { set_error("tcsfm_ssim_mean_fwd: null pointer"); return 1; }
+    if (N > 65535) { set_error("tcsfm_ssim_mean_fwd: N=%d exceeds 65535 planes", N); return 1; }
+    dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, N), block(kTileThreads);
+    const size_t smem = 2 * Tile<1>::kCells * sizeof(float);
+    cudaMemsetAsync(out_mean, 0, sizeof(float), (cudaStream_t)stream);
+    const float scale = (float)(1.0 / ((double)N * H * W));
+    TCSFM_LAUNCH(ssim_fwd_kernel<true>, grid, block, smem, stream, x, y, out_mean, H, W, kC1, kC2, scale);
+    return check_launch("tcsfm_ssim_mean_fwd");
 }
 
 extern "C" int tcsfm_ssim_bwd(const float* x, const float* y, const float* g_out, float* g_x, float* g_y,
@@ -125,6 +148,19 @@ extern "C" int tcsfm_ssim_bwd(const float* x, const float* y, const float* g_out
     if (N > 65535) { set_error("tcsfm_ssim_bwd: N=%d exceeds 65535 planes", N); return 1; }
     dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, N), block(kTileThreads);
     const size_t smem = (2 * Tile<2>::kCells + 4 * Tile<1>::kCells) * sizeof(float);
-    TCSFM_LAUNCH(ssim_bwd_kernel, grid, block, smem, stream, x, y, g_out, g_x, g_y, H, W, kC1, kC2);
+    TCSFM_LAUNCH(ssim_bwd_kernel, grid, block, smem, stream, x, y, g_out, (const float*)nullptr, 0.f, g_x, g_y, H, W, kC1, kC2);
     return check_launch("tcsfm_ssim_bwd");
+}
+
+extern "C" int tcsfm_ssim_mean_bwd(const float* x, const float* y, const float* g_mean, float* g_x, float* g_y,
+                                   int N, int H, int W, int flags, void* stream) {
+    (void)flags;
+    if (N <= 0 || H < 2 || W < 2) { set_error("tcsfm_ssim_mean_bwd: bad shape N=%d H=%d W=%d", N, H, W); return 1; }
+    if (!x || !y || !g_mean) { set_error("tcsfm_ssim_mean_bwd: null pointer"); return 1; }
+    if (N > 65535) { set_error("tcsfm_ssim_mean_bwd: N=%d exceeds 65535 planes", N); return 1; }
+    dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, N), block(kTileThreads);
+    const size_t smem = (2 * Tile<2>::kCells + 4 * Tile<1>::kCells) * sizeof(float);
+    const float scale = (float)(1.0 / ((double)N * H * W));
+    TCSFM_LAUNCH(ssim_bwd_kernel, grid, block, smem, stream, x, y, (const float*)nullptr, g_mean, scale, g_x, g_y, H, W, kC1, kC2);
+    return check_launch("tcsfm_ssim_mean_bwd");
 }

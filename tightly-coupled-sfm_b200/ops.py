@@ -54,12 +54,15 @@ class InverseWarp2Fn(torch.autograd.Function):
     pose-network input [target * valid_mask | projected_img] of train_mono.py:74-76."""
 
     @staticmethod
-    def forward(ctx, img, depth, ref_depth, kinv, proj, stack_target=None):
+    def forward(ctx, img, depth, ref_depth, kinv, proj, stack_target=None, need_depths=True):
+        # need_depths=False: projected_depth / computed_depth come back as None and are neither computed nor
+        # stored (solve_pose_iteratively only consumes the last iteration's, train_mono.py:69,80 vs :91)
         _require_cuda(img, depth, ref_depth, kinv, proj, stack_target)
         ctx.set_materialize_grads(False)
         ctx.flags = arith_flags(img.shape[0], img.shape[2], img.shape[3])
         with _guard(img):
-            outs = _raw.warp_fwd(lib(), img, depth, ref_depth, kinv, proj, ctx.flags, stack_target=stack_target)
+            outs = _raw.warp_fwd(lib(), img, depth, ref_depth, kinv, proj, ctx.flags, need_depths=need_depths,
+                                 stack_target=stack_target)
         ctx.save_for_backward(img, depth, ref_depth, kinv, proj)
         ctx.mark_non_differentiable(outs[1])
         return outs
@@ -68,12 +71,12 @@ class InverseWarp2Fn(torch.autograd.Function):
     def backward(ctx, g_img, g_valid, g_pd, g_cd, g_stack=None):
         img, depth, ref_depth, kinv, proj = ctx.saved_tensors
         need_img = ctx.needs_input_grad[0]
-        need_ref = ctx.needs_input_grad[2]
+        need_ref = ctx.needs_input_grad[2] and g_pd is not None      # ref_depth only feeds projected_depth
         with _guard(img):
             g_depth, g_ref, g_proj, g_src = _raw.warp_bwd(
                 lib(), img, depth, ref_depth, kinv, proj, g_img, g_pd, g_cd, ctx.flags,
                 need_img_grad=need_img, need_ref_depth_grad=need_ref, g_stack=g_stack)
-        return g_src, g_depth, g_ref, None, g_proj, None
+        return g_src, g_depth, g_ref, None, g_proj, None, None
 
 
 class SsimFn(torch.autograd.Function):
@@ -93,6 +96,48 @@ class SsimFn(torch.autograd.Function):
         with _guard(x):
             g_x, g_y = _raw.ssim_bwd(lib(), x, y, g_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ARITH_FLAGS)
         return g_x, g_y
+
+
+class SsimMeanFn(torch.autograd.Function):
+    """mean(SSIM dissimilarity map) of two [B,C,H,W] tensors as a [1] tensor: one launch forward (no
+    map in HBM), one backward (the depth-initialisation term of the PFT loss, optimizer.py:89-90)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        _require_cuda(x, y)
+        with _guard(x):
+            out = _raw.ssim_mean_fwd(lib(), x, y, ARITH_FLAGS)
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, y = ctx.saved_tensors
+        with _guard(x):
+            g_x, g_y = _raw.ssim_mean_bwd(lib(), x, y, g_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ARITH_FLAGS)
+        return g_x, g_y
+
+
+class PftReduceFn(torch.autograd.Function):
+    """(diff_img, valid_mask, auto_mask_error, auto_mask, weight_mask) stacked [2*S*B,1,H,W] -> the
+    reconstruction + depth-consistency part of the PFT loss (optimizer.py:45-86) as a [1] tensor;
+    kernels: csrc/pft_kernels.cu.  Differentiable w.r.t. diff_img and weight_mask."""
+
+    @staticmethod
+    def forward(ctx, diff, valid, auto_err, auto_mask, weight, bsz, n_src, flags, w_depth):
+        _require_cuda(diff, valid, auto_err, auto_mask, weight)
+        with _guard(diff):
+            loss, sums, maps = _raw.pft_reduce_fwd(lib(), diff, valid, auto_err, auto_mask, weight, bsz, n_src, flags, w_depth)
+        ctx.save_for_backward(sums, *maps)
+        ctx.cfg = (bsz, n_src, flags, w_depth)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        sums, maps = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        with _guard(sums):
+            g_diff, g_weight = _raw.pft_reduce_bwd(lib(), maps, sums, g_loss, *ctx.cfg)
+        return g_diff, None, None, None, g_weight, None, None, None, None
 
 
 class PairLossFn(torch.autograd.Function):
@@ -262,12 +307,12 @@ class PhotoErrorFn(torch.autograd.Function):
     weight_mask) of train_mono.py:84-92 in one launch; backward w.r.t. rec and the depths in one."""
 
     @staticmethod
-    def forward(ctx, tgt, src, rec, proj_depth, comp_depth, w_l1, w_ssim):
-        _require_cuda(tgt, src, rec, proj_depth, comp_depth)
+    def forward(ctx, tgt, src, rec, proj_depth, comp_depth, w_l1, w_ssim, valid=None):
+        _require_cuda(tgt, src, rec, proj_depth, comp_depth, valid)
         want_grad = any(ctx.needs_input_grad[2:5])
         with _guard(rec):
             auto_err, diff, auto_mask, weight, coef = _raw.photo_fwd(lib(), tgt, src, rec, proj_depth, comp_depth,
-                                                                     w_l1, w_ssim, ARITH_FLAGS, want_grad)
+                                                                     w_l1, w_ssim, ARITH_FLAGS, want_grad, valid=valid)
         if want_grad:
             ctx.save_for_backward(tgt, rec, proj_depth, comp_depth, coef)
             ctx.weights = (w_l1, w_ssim)
@@ -281,7 +326,7 @@ class PhotoErrorFn(torch.autograd.Function):
         with _guard(rec):
             g_rec, g_pd, g_cd = _raw.photo_bwd(lib(), tgt, rec, proj_depth, comp_depth, coef, g_diff, g_weight,
                                                ctx.weights[0], ctx.weights[1], ARITH_FLAGS)
-        return None, None, g_rec, g_pd, g_cd, None, None
+        return None, None, g_rec, g_pd, g_cd, None, None, None
 
 
 class SmoothLossFn(torch.autograd.Function):

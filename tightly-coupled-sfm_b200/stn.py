@@ -120,12 +120,13 @@ def inverse_warp2(img, depth, ref_depth, pose, intrinsics, padding_mode='zeros')
     return ops.InverseWarp2Fn.apply(img, depth, ref_depth, kinv, proj)
 
 
-def inverse_warp2_stacked(img, depth, ref_depth, pose, intrinsics, kinv, stack_target):
+def inverse_warp2_stacked(img, depth, ref_depth, pose, intrinsics, kinv, stack_target, need_depths=True):
     """inverse_warp2 plus the next pose-network input of solve_pose_iteratively
     (train_mono.py:74-76): returns (projected_img, valid_mask, projected_depth, computed_depth,
-    stack) with stack = [stack_target * valid_mask | projected_img] as one [B,6,H,W] tensor."""
+    stack) with stack = [stack_target * valid_mask | projected_img] as one [B,6,H,W] tensor.
+    need_depths=False skips the two depth outputs (returned as None) and their backward."""
     kinv, proj = projection_matrices(pose, intrinsics, kinv)
-    return ops.InverseWarp2Fn.apply(img, depth, ref_depth, kinv, proj, stack_target)
+    return ops.InverseWarp2Fn.apply(img, depth, ref_depth, kinv, proj, stack_target, need_depths)
 
 
 # ---- legacy helpers kept importable (no live callers in the reference) ----------

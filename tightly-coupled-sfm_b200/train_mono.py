@@ -72,18 +72,21 @@ def solve_pose_iteratively(num_iter, depths, pose_model, target_img, source_img_
     kinv = inverse_intrinsics(intrinsics_in).repeat(2 * n_src, 1, 1)
     tgt_view, src_view = imgs[:, 0:3], imgs[:, 3:6]
 
-    def warp(poses):
+    def warp(poses, last):
         # one launch: the reconstruction, its masks/depths and the next pose-net input
-        # [target * valid | reconstruction] (train_mono.py:69-76,80)
-        return inverse_warp2_stacked(src_view, tgt_depth_full, src_depth_full, -poses, intrinsics, kinv, tgt_view)
+        # [target * valid | reconstruction] (train_mono.py:69-76,80).  projected_depth / computed_depth are
+        # consumed by the return_errors block of the LAST iteration only (train_mono.py:91): the other
+        # iterations neither compute nor store them (8 B/px each way)
+        return inverse_warp2_stacked(src_view, tgt_depth_full, src_depth_full, -poses, intrinsics, kinv, tgt_view,
+                                     need_depths=return_errors and last)
 
     full_poses = pose_model(imgs)
     stacked = [full_poses.clone()]
-    img_rec, valid_mask, proj_d, comp_d, new_imgs = warp(full_poses)
-    for _ in range(num_iter - 1):
+    img_rec, valid_mask, proj_d, comp_d, new_imgs = warp(full_poses, num_iter == 1)
+    for it in range(num_iter - 1):
         full_poses = full_poses + pose_model(new_imgs)
         stacked.append(full_poses.clone())
-        img_rec, valid_mask, proj_d, comp_d, new_imgs = warp(full_poses)
+        img_rec, valid_mask, proj_d, comp_d, new_imgs = warp(full_poses, it == num_iter - 2)
     stacked = torch.stack(stacked, 1)                       # [2*S*B, num_iter, 6]
 
     outputs = {'fwd': {}, 'inv': {}}
