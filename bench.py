@@ -61,7 +61,15 @@ LOSS_CFG = {"l1_weight": 0.15, "l_ssim_weight": 0.85, "l_smooth_weight": 0.05, "
             "l_depth_consist_weight": 0.14, "min_depth": 0.06, "max_depth": 2.67, "l_smooth": False,
             "l_reconstruction": True, "l_inverse": True, "l_depth_consist": True,
             "with_auto_mask": True, "l_ssim": True, "with_depth_mask": True}
+TRAIN_WORKLOADS = {
+    # BASELINE config 5: the training-step loss path at 4 scales up to 376x1242 (every scale nearest-upsampled to full
+    # resolution, losses.py:86-87), 4 egomotion iterations, the paper's training flags (run_mono_training.py:50-64)
+    "train376x4": dict(b=2, h=376, w=1242, scales=4, iterations=4, full=False,
+                       desc="train_step_b2_376x1242_4scales_4iter_standin_nets_adam"),
+}
 METRIC = "warp+SSIM/L1 loss fwd+bwd frames/s at 192x640"
+ARITH_MODES = ("exact", "fast")
+DEFAULT_ARITH = "exact"
 N_INPUT_SETS = 8      # rotating input sets: 8 x ~47 MB > 126 MB of L2, so no step finds its inputs in L2
 
 
@@ -75,6 +83,12 @@ def make_inputs(wl, seed, device, pin=False):
         base = torch.tensor(synth.KITTI_K, dtype=torch.float32)
     else:
         base = synth.scaled_intrinsics(wl["h"], wl["w"], synth.SCANNET_K, (256, 320))
+    # every input set carries its own intrinsics (focal lengths / principal point jittered by up to 1 %), so a
+    # step that reused a stale K^-1 would be caught: K^-1 is recomputed inside every timed step (models/stn.py:257)
+    base = base.clone()
+    base[0, 0] *= 1.0 + 0.002 * (seed % 5)
+    base[1, 1] *= 1.0 + 0.002 * (seed % 3)
+    base[0, 2] += 0.25 * (seed % 4)
     fr = synth.make_frames(wl["b"], wl["h"], wl["w"], n_src=wl["n_src"], seed=seed, depth_range=rng, intrinsics=base)
     flat = {"target": fr["target"], "K": fr["K"]}
     for j in range(wl["n_src"]):
@@ -168,67 +182,80 @@ def cpu_port_throughput(wl, steps, warmup, threads):
     return wl["b"] * steps / dt, dt / steps * 1e3
 
 
-def main_pft(args):
-    """PFT frames/s: every rank optimises its own contiguous shard of window minibatches
-    (tcsfm_b200.shard), no communication; a 'step' is one window minibatch taken through all
-    optimisation epochs (depth-net -> solve_pose_iteratively -> loss -> backward -> Adam)."""
-    wl = PFT_WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    from tcsfm_b200 import pft_driver, shard, synth
+class Ranks:
+    """One process per GPU (torchrun): rank bookkeeping, barrier and max-over-ranks of device times."""
+
+    def __init__(self, need_cuda=True):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        self.dev = None
+        if need_cuda:
+            torch.cuda.set_device(self.local_rank)
+            self.dev = torch.device("cuda", self.local_rank)
+            if self.world > 1:
+                import torch.distributed as dist
+                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+                dist.init_process_group("nccl", device_id=self.dev)
+                self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms(self, *values):
+        if self.dist is None:
+            return list(values)
+        t = torch.tensor(list(values), device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def timed(self, fn, steps):
+        """Device time (CUDA events on the launching stream) of `steps` calls, bracketed by barrier +
+        synchronize on both sides, max over ranks."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        return self.max_ms(e0.elapsed_time(e1))[0]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def pft_measure(R, name, steps, warm, no_graph=False, sequence_frames=0):
+    """PFT frames/s on this rank's shard of window minibatches (tcsfm_b200.shard), no communication; a 'step' is one
+    window minibatch taken through all optimisation epochs (depth-net -> solve_pose_iteratively -> loss -> backward
+    -> Adam; optimizer.py:136-297 with stand-in networks).  Returns the sub-object for the JSON line.
+
+    sequence_frames > 0 additionally runs BASELINE config 4: a whole synthetic sequence of that many frames
+    (1591 = KITTI seq 09 -> 795 windows -> 133 minibatches, the last of 3 windows), its minibatches sharded
+    contiguously over the ranks -- total work fixed, i.e. strong scaling."""
+    from tcsfm_b200 import _timing, pft_driver, shard, synth
+    wl = PFT_WORKLOADS[name]
+    dev = R.dev
     opts = {"epochs": wl["epochs"], "num_source_imgs": wl["n_src"]}
     rng = synth.KITTI_DEPTH_RANGE if wl["h"] == 192 else synth.SCANNET_DEPTH_RANGE
     base = synth.KITTI_K if wl["h"] == 192 else synth.SCANNET_K
-    steps = min(args.steps, 4)
-    warm = max(1, min(args.warmup, 1))
 
-    def frames_for(seed, device):
-        return synth.make_frames(wl["b"], wl["h"], wl["w"], n_src=wl["n_src"], seed=seed, depth_range=rng,
-                                 intrinsics=torch.tensor(base, dtype=torch.float32), device=device)
+    def frames_for(seed, b=wl["b"]):
+        k = torch.tensor(base, dtype=torch.float32)
+        k[0, 0] *= 1.0 + 0.002 * (seed % 5)                      # windows do not share intrinsics bit for bit
+        return synth.make_frames(b, wl["h"], wl["w"], n_src=wl["n_src"], seed=seed, depth_range=rng, intrinsics=k, device=dev)
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        from oracle import ref_torch as O
-
-        class OracleBackend:
-            solve_pose_iteratively = staticmethod(O.iterative_pose)
-            compute_optimization_loss = staticmethod(O.pft_window_loss)
-            disp_to_depth = staticmethod(O.disp_to_depth)
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        cpu_opts = dict(opts, epochs=2)
-        fr = frames_for(0, "cpu")
-        dn, pn = synth.TinyDepthNet(0), synth.TinyPoseNet(0)
-        t0 = time.perf_counter()
-        pft_driver.optimize_window(dn, pn, fr["target"], fr["sources"], fr["K"], cpu_opts, wl["iterations"], rng, OracleBackend)
-        dt = (time.perf_counter() - t0) * wl["epochs"] / cpu_opts["epochs"]
-        fps = wl["b"] / dt
-        emit(({"impl": "reference", "metric": "PFT frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-                          "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"]},
-                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                           "sample": "2 of %d epochs of one window minibatch, extrapolated" % wl["epochs"]},
-                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    from tcsfm_b200 import _timing
     depth_net, pose_net = synth.TinyDepthNet(0).to(dev), synth.TinyPoseNet(0).to(dev)
-    total_mbs = steps * world
-    lo, hi = shard.shard_range(total_mbs, rank, world)           # this rank's window minibatches
-    data = [frames_for(1000 + i, dev) for i in range(lo, hi)]
+    total_mbs = steps * R.world
+    lo, hi = shard.shard_range(total_mbs, R.rank, R.world)           # this rank's window minibatches
+    data = [frames_for(1000 + i) for i in range(lo, hi)]
     host = [{k: ([t.cpu().pin_memory() for t in v] if isinstance(v, list) else v.cpu().pin_memory()) for k, v in d.items()}
             for d in data[:2]]
-
-    runner = None if args.no_graph else pft_driver.WindowRunner(depth_net, pose_net, opts, wl["iterations"], rng)
+    runner = None if no_graph else pft_driver.WindowRunner(depth_net, pose_net, opts, wl["iterations"], rng)
 
     def run(fr):
         if runner is not None:        # epoch graphs captured on the first (warm-up) window, replayed afterwards
@@ -236,63 +263,115 @@ def main_pft(args):
         return pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts,
                                           wl["iterations"], rng)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(warm):
+    for i in range(max(1, warm)):
         run(data[i % len(data)])
-    barrier()
     l0 = _timing.LAUNCH_COUNT
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for fr in data:
-        run(fr)
-    e1.record()
-    barrier()
+    ms = R.timed(lambda i: run(data[i]), len(data))
     launches = _timing.LAUNCH_COUNT - l0
-    ms = e0.elapsed_time(e1)
-    # end to end: window inputs from pinned host memory, the final loss read back
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for i in range(len(data)):
+
+    def e2e_step(i):        # window inputs from pinned host memory, the final loss read back
         h = host[i % len(host)]
         fr = {k: ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v.to(dev, non_blocking=True))
               for k, v in h.items() if k in ("target", "sources", "K")}
         float(run(fr)["losses"][-1])
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
-    # device time of the library's own launches inside one window minibatch (the hot path proper)
+    ms_e2e = R.timed(e2e_step, len(data))
+    # device time of the library's own launches inside one window minibatch (the hot path proper) against
+    # the device time of the whole window, both eager (events recorded during graph capture cannot be timed)
     timer = _timing.KernelTimer()
-    with _timing.record(timer):                 # eager: events recorded during graph capture cannot be timed
+    torch.cuda.synchronize()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    with _timing.record(timer):
         pft_driver.optimize_window(depth_net, pose_net, data[0]["target"], data[0]["sources"], data[0]["K"], opts,
                                    wl["iterations"], rng, cuda_graph=False)
+    w1.record()
     ksum = timer.summary()
+    eager_window_ms = w0.elapsed_time(w1)
     hot_ms = sum(v["launches"] * v["avg_ms"] for v in ksum.values())
-    if dist is not None:
-        t = torch.tensor([ms, ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
-        dist.destroy_process_group()
-    if rank != 0:
-        return
     frames = wl["b"] * total_mbs
     h2d = sum(t.numel() * 4 for t in [host[0]["target"], host[0]["K"]] + host[0]["sources"])
-    emit(({"metric": "PFT frames/s", "value": frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world,
-                      "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": wl["desc"], "window_minibatches_per_gpu": steps, "parallelism": "shard%d" % world,
-                                 "networks": "stand-in TinyDepthNet/TinyPoseNet (the reference nets are out of scope)",
-                                 "launch": "eager" if args.no_graph else "epoch CUDA graphs captured on the warm-up window, replayed for every timed window"},
-                      "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                              "d2h_bytes_per_step": 4},
-                      "gpu_launches": launches,
-                      "hot_path": {"ms_per_window_minibatch": hot_ms, "frames_per_s": wl["b"] / (hot_ms / 1e3),
-                                   "note": "sum of the library launches' device time (CUDA events), networks/optimiser excluded",
-                                   "kernels": ksum}}))
+    out = {"metric": "PFT frames/s", "value": frames / (ms / 1e3), "unit": "frames/s", "workload": wl["desc"],
+           "window_minibatches_per_gpu": steps, "ms_per_window_minibatch": ms / steps, "scaling": "weak",
+           "launch": "eager" if no_graph else "epoch CUDA graphs captured on the warm-up window, replayed for every timed window",
+           "networks": "stand-in TinyDepthNet/TinyPoseNet (the reference nets are out of scope)",
+           "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+           "gpu_launches": launches,
+           "hot_path": {"ms_per_window_minibatch": hot_ms, "frames_per_s": wl["b"] / (hot_ms / 1e3),
+                        "share_of_eager_window_device_time": hot_ms / eager_window_ms,
+                        "note": "sum of the library launches' device time (CUDA events) over one eager window minibatch; "
+                                "the rest is the stand-in networks, Adam and PyTorch's own glue",
+                        "kernels": ksum}}
+    if sequence_frames:
+        mbs = shard.window_minibatches(sequence_frames, stride=2, minibatch=wl["b"])
+        s_lo, s_hi = shard.shard_range(len(mbs), R.rank, R.world)
+        pool = data + [frames_for(5000 + i) for i in range(max(0, 4 - len(data)))]
+        short = {}
+
+        def seq_step(i):
+            n_win = len(mbs[s_lo + i])
+            if n_win == wl["b"]:
+                run(pool[i % len(pool)])
+            else:                                               # the ragged last minibatch: eager, its own batch size
+                if n_win not in short:
+                    short[n_win] = frames_for(7000 + n_win, b=n_win)
+                fr = short[n_win]
+                pft_driver.optimize_window(depth_net, pose_net, fr["target"], fr["sources"], fr["K"], opts, wl["iterations"], rng)
+        ms_seq = R.timed(seq_step, s_hi - s_lo)
+        out["sequence"] = {"frames": sequence_frames, "windows": sum(len(m) for m in mbs), "window_minibatches": len(mbs),
+                           "minibatches_this_rank": s_hi - s_lo, "seconds": ms_seq / 1e3,
+                           "sequence_frames_per_s": sequence_frames / (ms_seq / 1e3),
+                           "windows_per_s": sum(len(m) for m in mbs) / (ms_seq / 1e3), "scaling": "strong",
+                           "note": "BASELINE config 4: contiguous minibatch ranges per GPU, no inter-GPU traffic"}
+    return out
+
+
+def main_pft(args):
+    wl = PFT_WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        from oracle import ref_torch as O
+        from tcsfm_b200 import pft_driver, synth
+
+        class OracleBackend:
+            solve_pose_iteratively = staticmethod(O.iterative_pose)
+            compute_optimization_loss = staticmethod(O.pft_window_loss)
+            disp_to_depth = staticmethod(O.disp_to_depth)
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        rng = synth.KITTI_DEPTH_RANGE if wl["h"] == 192 else synth.SCANNET_DEPTH_RANGE
+        base = synth.KITTI_K if wl["h"] == 192 else synth.SCANNET_K
+        cpu_opts = {"epochs": 2, "num_source_imgs": wl["n_src"]}
+        fr = synth.make_frames(wl["b"], wl["h"], wl["w"], n_src=wl["n_src"], seed=0, depth_range=rng,
+                               intrinsics=torch.tensor(base, dtype=torch.float32))
+        dn, pn = synth.TinyDepthNet(0), synth.TinyPoseNet(0)
+        t0 = time.perf_counter()
+        pft_driver.optimize_window(dn, pn, fr["target"], fr["sources"], fr["K"], cpu_opts, wl["iterations"], rng, OracleBackend)
+        dt = (time.perf_counter() - t0) * wl["epochs"] / cpu_opts["epochs"]
+        fps = wl["b"] / dt
+        emit(({"impl": "reference", "metric": "PFT frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+               "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"]},
+               "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": "2 of %d epochs of one window minibatch, extrapolated" % wl["epochs"]},
+               "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    R = Ranks()
+    steps = min(args.steps, 4)
+    warm = max(1, min(args.warmup, 1))
+    sub = pft_measure(R, args.workload, steps, warm, args.no_graph, sequence_frames=args.sequence_frames)
+    R.close()
+    if R.rank != 0:
+        return
+    line = {"metric": sub["metric"], "value": sub["value"], "unit": "frames/s", "n_gpus": R.world, "steps": steps,
+            "warmup": warm, "ms_per_step": sub["ms_per_window_minibatch"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": sub["workload"], "window_minibatches_per_gpu": steps, "parallelism": "shard%d" % R.world,
+                       "networks": sub["networks"], "launch": sub["launch"]},
+            "e2e": sub["e2e"], "gpu_launches": sub["gpu_launches"], "hot_path": sub["hot_path"]}
+    if "sequence" in sub:
+        line["sequence"] = sub["sequence"]
+    emit(line)
 
 
 def main_sweep(args):
@@ -347,107 +426,163 @@ def main_sweep(args):
     emit(line)
 
 
+def train_measure(R, steps, warm, wl_name="train376x4"):
+    """Training mode (BASELINE config 5): one minibatch of Trainer.forward (train_mono.py:159-194) per step around the
+    fused loss at 4 scales, stand-in networks of the reference's parameter volume (15.7 M fp32 = 62.8 MB of
+    gradients), Adam; with more than one rank DistributedDataParallel all-reduces the network gradients over NCCL --
+    the only collective of the mode.  Reports the step with and without the all-reduce (`no_sync`) and the bare
+    all-reduce of the same payload, so the exposed (non-overlapped) NCCL time is visible."""
+    from tcsfm_b200 import _timing, synth, training
+    wl = TRAIN_WORKLOADS[wl_name]
+    dev = R.dev
+    cfg = training.default_config(num_scales=wl["scales"], iterations=wl["iterations"], full_profile=wl["full"])
+    step, optim = training.make_step(cfg, seed=0, device=dev, padded=True)
+    model = training.wrap_ddp(step, dev) if R.dist is not None else step
+    k = torch.tensor(synth.KITTI_FULL_K if wl["h"] == 376 else synth.KITTI_K, dtype=torch.float32)
+    data = [synth.make_frames(wl["b"], wl["h"], wl["w"], n_src=2, seed=300 + 10 * R.rank + i, intrinsics=k, device=dev)
+            for i in range(4)]
+    n_params = sum(p.numel() for p in step.parameters())
+    for i in range(max(3, warm)):
+        training.run_train_step(model, optim, data[i % 4])
+    l0 = _timing.LAUNCH_COUNT
+    ms_sync = R.timed(lambda i: training.run_train_step(model, optim, data[i % 4], sync=True), steps)
+    launches = _timing.LAUNCH_COUNT - l0
+    ms_nosync = R.timed(lambda i: training.run_train_step(model, optim, data[i % 4], sync=False), steps)
+    out = {"metric": "training-step frames/s (loss at %d scales, %dx%d)" % (wl["scales"], wl["h"], wl["w"]),
+           "workload": wl["desc"], "value": wl["b"] * R.world * steps / (ms_sync / 1e3), "unit": "frames/s",
+           "batch_per_gpu": wl["b"], "steps": steps, "ms_per_step": ms_sync / steps, "scaling": "weak",
+           "ms_per_step_without_allreduce": ms_nosync / steps,
+           "exposed_allreduce_ms_per_step": max(0.0, (ms_sync - ms_nosync) / steps),
+           "gradient_bytes_per_step": 4 * n_params, "gpu_launches": launches,
+           "collective": ("DistributedDataParallel: NCCL all-reduce (mean) of the network gradients, %d ranks" % R.world)
+           if R.dist is not None else "none (single rank)",
+           "networks": "stand-in depth/pose networks padded to the reference's %d parameters" % n_params,
+           "launch": "eager"}
+    if R.dist is not None:
+        flat = torch.zeros(n_params, device=dev)
+        for _ in range(3):
+            R.dist.all_reduce(flat)
+        ms_ar = R.timed(lambda i: R.dist.all_reduce(flat), 10)
+        out["bare_allreduce_ms"] = ms_ar / 10
+        out["bare_allreduce_busbw_GBps"] = 4 * n_params * 2 * (R.world - 1) / R.world / (ms_ar / 10 * 1e-3) / 1e9
+    return out
+
+
+def eager_cuda_measure(wl, sets, cfg, steps):
+    """The reference's eager PyTorch path (the oracle's op-for-op restatement: the same ATen CUDA kernels in the same
+    order, including mean_on_mask's host synchronisation) on the same B200 -- the bar a user of the reference sees."""
+    from oracle import ref_torch as O
+    n_src, n_scales = wl["n_src"], wl.get("scales", 1)
+
+    def step(i):
+        inp = sets[i % len(sets)]
+        disps = [[inp["disp%d" % j].detach().clone().requires_grad_(True)] +
+                 [inp["disp%d_s%d" % (j, sc)].detach().clone().requires_grad_(True) for sc in range(1, n_scales)]
+                 for j in range(1 + n_src)]
+        poses = [inp["pose%d" % j].detach().clone().requires_grad_(True) for j in range(n_src)]
+        poses_inv = [inp["pose_inv%d" % j].detach().clone().requires_grad_(True) for j in range(n_src)]
+        out = O.compute_loss(cfg, [inp["source%d" % j] for j in range(n_src)], inp["target"], [poses, poses_inv], disps, inp["K"])
+        out["total"].sum().backward()
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": wl["b"] / (ms / 1e3), "unit": "frames/s", "ms_per_step": ms, "steps": steps, "kind": "port",
+            "what": "oracle/ref_torch.py (the reference's ATen operator sequence) run eagerly on the same GPU, "
+                    "CUDA events, inputs resident"}
+
+
+def base_config(args, wl, world):
+    """The `config` object of the JSON line -- identical for the two arms (`--impl ours|reference`)."""
+    cfg = {"workload": wl["desc"], "batch_per_gpu": wl["b"],
+           "pairs_per_step_per_gpu": 2 * wl["n_src"] * wl["b"] * wl.get("scales", 1),
+           "height": wl["h"], "width": wl["w"], "flags": "full (depth-consistency mask + term, auto-mask, SSIM+L1)",
+           "parallelism": "shard%d" % max(world, args.gpus),
+           "l2": "inputs rotate over %d sets (> L2 capacity), each with its own intrinsics" % N_INPUT_SETS,
+           "launch": "eager" if args.no_graph else "cuda-graph replay of the full step (one graph per input set)",
+           "arithmetic": args.arith}
+    if args.profile == "train":
+        cfg["flags"] = "paper training defaults (auto-mask, SSIM+L1; no depth-consistency mask/term)"
+    return cfg
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 2000 ours, 20 reference arm)")
+    ap.add_argument("--warmup", type=int, default=None, help="warm-up steps (default: 50 ours, 3 reference arm)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS) + sorted(PFT_WORKLOADS) + ["sweep"])
     ap.add_argument("--cpu-steps", type=int, default=None, help="steps of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of replaying CUDA graphs")
-    ap.add_argument("--ddp-allreduce-mb", type=float, default=0.0,
-                    help="multi-GPU only: after every step all-reduce a buffer of this many MB over NCCL, standing in "
-                         "for DDP's exchange of the network gradients (62.9 MB for the reference's nets, SURVEY.md §5); "
-                         "the loss path itself has no collective.  Implies eager launches.")
     ap.add_argument("--sweep-evals", type=int, default=100, help="workload 'sweep': evaluations per surface")
     ap.add_argument("--profile", default="full", choices=["full", "train"],
                     help="loss flags: 'full' = depth-consistency mask + term on (what PFT uses, 84 B/px/pair), "
                          "'train' = the paper's training defaults (run_mono_training.py:50-64: both off)")
+    ap.add_argument("--arith", default=DEFAULT_ARITH, choices=sorted(ARITH_MODES),
+                    help="SSIM arithmetic of the pair kernels: 'exact' keeps every rounding step of eager PyTorch; "
+                         "'fast' keeps geometry, warp and masks bit-exact and evaluates the SSIM statistics at tolerance level")
+    ap.add_argument("--only", default=None, choices=["loss"], help="'loss': skip the pft / train / eager-CUDA sub-benchmarks")
+    ap.add_argument("--sequence-frames", type=int, default=0, help="PFT workloads: also time a whole sequence of this many frames")
     args = ap.parse_args()
+    ref_arm = args.impl == "reference"
+    if args.steps is None:
+        args.steps = 20 if ref_arm else 2000
+    if args.warmup is None:
+        args.warmup = 3 if ref_arm else 50
     if args.workload in PFT_WORKLOADS:
         return main_pft(args)
     if args.workload == "sweep":
         return main_sweep(args)
     wl = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    config = {"workload": wl["desc"], "batch_per_gpu": wl["b"],
-              "pairs_per_step_per_gpu": 2 * wl["n_src"] * wl["b"] * wl.get("scales", 1),
-              "height": wl["h"], "width": wl["w"], "flags": "full (depth-consistency mask + term, auto-mask, SSIM+L1)",
-              "parallelism": "shard%d" % max(world, args.gpus),
-              "l2": "inputs rotate over %d sets (> L2 capacity)" % N_INPUT_SETS}
 
-    if args.impl == "reference":
-        if rank != 0:
+    if ref_arm:
+        # the reference's own CPU implementation of the path (oracle port: the same ATen kernels in the same order),
+        # all host threads, the arm's --steps / --warmup honoured as given
+        if int(os.environ.get("RANK", "0")) != 0:
             return
-        steps = max(1, min(args.steps, args.cpu_steps or 6))
-        warm = max(1, min(args.warmup, 1))
-        fps, ms = cpu_port_throughput(wl, steps, warm, cores)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        config = base_config(args, wl, world)
+        fps, ms = cpu_port_throughput(wl, args.steps, args.warmup, cores)
         line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-                "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": "%d steps of the same B=%d minibatch, oracle port of the reference's "
-                                           "PyTorch CPU path, torch threads=%d" % (steps, wl["b"], cores)},
+                                           "PyTorch CPU path, torch threads=%d" % (args.steps, wl["b"], cores)},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    R = Ranks()
+    rank, world, dev = R.rank, R.world, R.dev
+    config = base_config(args, wl, world)
 
-    from tcsfm_b200 import _timing, losses, synth
+    from tcsfm_b200 import _timing, losses, ops, synth
+    ops.set_arithmetic(args.arith)
     kitti = wl["h"] in (192, 376)
     rng = synth.KITTI_DEPTH_RANGE if kitti else synth.SCANNET_DEPTH_RANGE
     flags_cfg = {} if args.profile == "full" else {"l_depth_consist": False, "with_depth_mask": False}
-    if args.profile == "train":
-        config["flags"] = "paper training defaults (auto-mask, SSIM+L1; no depth-consistency mask/term)"
-    loss_mod = losses.Compute_Loss(dict(LOSS_CFG, num_scales=wl.get("scales", 1), min_depth=rng[0], max_depth=rng[1],
-                                        **flags_cfg))
+    loss_cfg = dict(LOSS_CFG, num_scales=wl.get("scales", 1), min_depth=rng[0], max_depth=rng[1], **flags_cfg)
+    loss_mod = losses.Compute_Loss(loss_cfg)
     n_src = wl["n_src"]
     sets = [make_inputs(wl, 100 * rank + s, dev) for s in range(N_INPUT_SETS)]
     host_sets = [make_inputs(wl, 100 * rank + s, dev, pin=True) for s in range(2)]
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms
-
-    # The resident-input arm replays one captured CUDA graph per input set (the step has no
-    # host-side control flow: the mean-on-mask threshold is decided on the device), so the
-    # timed region contains exactly the device work of K full steps.
+    # The resident-input arm replays one captured CUDA graph per input set (the step has no host-side control flow:
+    # the mean-on-mask threshold is decided on the device, K^-1 is computed inside the step without a host check), so
+    # the timed region contains exactly the device work of K full steps.
     graphs = None
-    grad_buf = None
-    if args.ddp_allreduce_mb > 0 and dist is not None:
-        grad_buf = torch.zeros(int(args.ddp_allreduce_mb * 1e6 / 4), device=dev)
-        args.no_graph = True
-        config["collective"] = "NCCL all-reduce of %.1f MB per step (DDP stand-in)" % args.ddp_allreduce_mb
     if not args.no_graph:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -463,22 +598,16 @@ def main():
             with torch.cuda.graph(g_):
                 out_ = run_step(loss_mod, s_, n_src)
             graphs.append((g_, out_))
-        config["launch"] = "cuda-graph replay of the full step (one graph per input set)"
-    else:
-        config["launch"] = "eager"
 
     def step_resident(i):
         if graphs is not None:
             graphs[i % N_INPUT_SETS][0].replay()
         else:
             run_step(loss_mod, sets[i % N_INPUT_SETS], n_src)
-            if grad_buf is not None:
-                dist.all_reduce(grad_buf)
 
-    # End-to-end arm: every step copies its inputs from pinned host memory and reads the loss
-    # back to the host.  Two device-side input buffers are used so that the copy of step i+1
-    # (copy stream) overlaps the compute of step i (graph replay on the main stream); the loss
-    # of step i is read on the host while step i+1 runs.
+    # End-to-end arm: every step copies its inputs from pinned host memory and reads the loss back to the host.  Two
+    # device-side input buffers are used so that the copy of step i+1 (copy stream) overlaps the compute of step i
+    # (graph replay on the main stream); the loss of step i is read on the host while step i+1 runs.
     loss_holder = [0.0]
     e2e = None
     if graphs is not None:
@@ -514,33 +643,70 @@ def main():
 
     for i in range(args.warmup):
         step_resident(i)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(R.local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     launches0 = _timing.LAUNCH_COUNT
-    ms_total = timed(step_resident, args.steps)
+    ms_total = R.timed(step_resident, args.steps)
     launches = _timing.LAUNCH_COUNT - launches0
     clocks = sampler.summary() if sampler else None
 
     # per-launch device time of the library calls, live over a second (eager) pass of the same steps
     def step_eager(i):
         run_step(loss_mod, sets[i % N_INPUT_SETS], n_src)
+    eager_steps = min(args.steps, 50)
     l0 = _timing.LAUNCH_COUNT
     timer = _timing.KernelTimer()
     with _timing.record(timer):
-        timed(step_eager, min(args.steps, 50))
+        R.timed(step_eager, eager_steps)
     ksum = timer.summary()
     if graphs is not None:       # launches inside a replayed graph are not seen by the Python counter
-        launches = (_timing.LAUNCH_COUNT - l0) // min(args.steps, 50) * args.steps
+        launches = (_timing.LAUNCH_COUNT - l0) // eager_steps * args.steps
 
     for i in range(min(args.warmup, 5)):
         step_e2e(i)
     e2e_steps = max(5, min(args.steps, 500))
-    ms_e2e = timed(step_e2e, e2e_steps)
+    ms_e2e = R.timed(step_e2e, e2e_steps)
+    # restore the resident buffers the e2e arm overwrote (sets 0 and 1 double as its staging buffers)
+    with torch.no_grad():
+        for k_ in range(2):
+            fresh = make_inputs(wl, 100 * rank + k_, dev)
+            for name, t in fresh.items():
+                sets[k_][name].copy_(t)
 
+    sub = {}
+    if args.only is None and args.workload == "kitti":
+        # driver-visible numbers for the other two modes of BASELINE.json's metric / configs 3-5
+        pft_steps = max(1, min(args.steps, 3))
+        sub["pft"] = pft_measure(R, "pft", pft_steps, 1, sequence_frames=1591)
+        sub["pft_scannet"] = pft_measure(R, "pft-scannet", pft_steps, 1)
+        sub["train_ddp" if world > 1 else "train"] = train_measure(R, max(3, min(args.steps, 10)), 3)
+    other = None
+    alt = "exact" if args.arith == "fast" else "fast"
+    if args.only is None and rank == 0 and args.workload == "kitti" and alt in ops.PAIR_ARITHMETICS:
+        # the same workload through the other SSIM arithmetic flavour (both are reported every run)
+        ops.set_arithmetic(alt)
+        for i in range(5):
+            step_eager(i)
+        t_alt = _timing.KernelTimer()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with _timing.record(t_alt):
+            a0.record()
+            for i in range(eager_steps):
+                step_eager(i)
+            a1.record()
+        k_alt = t_alt.summary()
+        other = {"arithmetic": alt, "launch": "eager", "ms_per_step": a0.elapsed_time(a1) / eager_steps,
+                 "value": wl["b"] / (a0.elapsed_time(a1) / eager_steps / 1e3), "unit": "frames/s",
+                 "kernels": {k: v for k, v in k_alt.items() if k.startswith("pair_loss")}}
+        ops.set_arithmetic(args.arith)
+    eager_cuda = None
+    if args.only is None and rank == 0:
+        eager_cuda = eager_cuda_measure(wl, sets, loss_cfg, max(20, min(args.steps, 50)))
+    R.barrier()
+    R.close()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
         return
 
     frames = wl["b"] * world
@@ -564,14 +730,15 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.isfile(tpath) and args.workload == "kitti":
-            traffic = json.load(open(tpath)).get(dom)          # dram read+write per launch from the committed ncu capture
+            traffic = json.load(open(tpath)).get(args.arith, {}).get(dom)   # dram read+write per launch, committed ncu capture
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": ksum[dom]["avg_ms"],
                     "algorithmic_bytes_per_launch": bytes_per_launch[dom],
                     "step_algorithmic_GBps": 84 * npx * pairs / (ms_total / args.steps * 1e-3) / 1e9,
+                    "step_frac": 84 * npx * pairs / (ms_total / args.steps * 1e-3) / 1e9 / peak,
                     "kernels": ksum}
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         csteps = args.cpu_steps or 4
         cfps, cms = cpu_port_throughput(wl, csteps, 1, cores)
         cpu_baseline = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port", "ms_per_step": cms,
@@ -583,11 +750,12 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "pairs_per_s": value * 2 * n_src, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "h2d_GBps_per_gpu": h2d / (ms_e2e / e2e_steps * 1e-3) / 1e9},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "eager_cuda_baseline": eager_cuda, "other_arithmetic": other}
+    line.update(sub)
     emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -686,8 +686,12 @@ def test_graph_replay_follows_changed_intrinsics():
     graph.replay()
     got, got_grad = static_total.detach().clone(), disps[0].grad.clone()
     ref = step()
-    assert torch.equal(got, ref.detach())
-    assert rel_l2(got_grad, disps[0].grad) < 1e-6
+    # (the masked sums are accumulated with atomics: equal up to their run-to-run rounding order)
+    assert abs(float(got) - float(ref)) <= 2e-6 * abs(float(ref)), (float(got), float(ref))
+    assert rel_l2(got_grad, disps[0].grad) < 1e-5
+    stale = O.compute_loss(goldens.FULL_CFG, fr["sources"], fr["target"], [fr["poses"], fr["poses_inv"]],
+                           [[d.detach()] for d in fr["disps"]], fr["K"])
+    assert abs(float(got) - float(stale["total"])) > 1e-4 * abs(float(got)), "the changed K must change the loss"
     fresh = [leaf(d) for d in fr["disps"]]
     out = O.compute_loss(goldens.FULL_CFG, fr["sources"], fr["target"], [fr["poses"], fr["poses_inv"]],
                          [[d] for d in fresh], K2)

@@ -16,6 +16,20 @@ from ._lib import lib
 ARITH_FLAGS = 0
 
 
+# SSIM arithmetic of the fused pair loss: "exact" keeps every rounding step of eager PyTorch (bit-identical
+# diff_img / SSIM maps); "fast" (when the library provides it) keeps geometry, warp, L1 and every mask bit-exact
+# and evaluates the 3x3 SSIM statistics at tolerance level (loss <= 1e-5, gradients <= 1e-4 of the reference).
+PAIR_ARITHMETIC = "exact"
+PAIR_ARITHMETICS = ("exact",)
+
+
+def set_arithmetic(mode):
+    global PAIR_ARITHMETIC
+    if mode not in PAIR_ARITHMETICS:
+        raise NotImplementedError("pair-loss arithmetic %r is not available (have %s)" % (mode, ", ".join(PAIR_ARITHMETICS)))
+    PAIR_ARITHMETIC = mode
+
+
 def arith_flags(batch, height, width):
     """Arithmetic flavour of a launch standing in for reference calls with `batch` pairs: eager
     CUDA bmm runs a non-fused kernel for batch 1 while m*n*k = 9*H*W <= 2^21 (bisected on the
