@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 8
+#define TCSFM_ABI_VERSION 9
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -46,6 +46,12 @@ extern "C" {
  * torch.inverse returns K^-1 column-major; profiles/r01_probe_bmm*.json, r01_probe_b1_calls.json.)
  * Set by the Python layer when the reference would have issued such a call. */
 #define TCSFM_ARITH_BMM_NOFMA  (1 << 6)
+/* "fast" arithmetic of the fused pair loss: geometry, bilinear sample, validity mask, the L1 term and the auto-mask
+ * comparison of losses.py:158 keep the exact roundings selected above; the 3x3 SSIM statistics, the SSIM ratio and the
+ * depth-inconsistency ratio are evaluated with separable sums, fused multiply-adds and approximate reciprocals
+ * (tolerance level: loss 1e-5, gradients 1e-4 of the reference; BASELINE.json north_star).  The workspace then has the
+ * layout / size tcsfm_pair_ws_floats() reports. */
+#define TCSFM_ARITH_FAST       (1 << 7)
 /* pair-loss configuration (losses.py:65-73,151-183 config keys) */
 #define TCSFM_AUTO_MASK        (1 << 1)   /* with_auto_mask   */
 #define TCSFM_SSIM             (1 << 2)   /* l_ssim           */
@@ -135,6 +141,9 @@ typedef struct tcsfm_pair_group {
 } tcsfm_pair_group;
 
 int tcsfm_pair_coef_planes(void);
+/* floats of workspace per pair (one batch element of one group) for the arithmetic selected in `flags`:
+ * coef of a group is [B, tcsfm_pair_ws_floats(H, W, flags)], 16-byte aligned. */
+int64_t tcsfm_pair_ws_floats(int H, int W, int flags);
 int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
                         int B, int H, int W, float w_l1, float w_ssim, int flags, void* stream);
 int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,

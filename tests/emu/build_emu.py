@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "tightly-coupled-sfm_b200", "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libtcsfm_emu.so")
-SOURCES = ["cabi.cu", "warp_kernels.cu", "ssim_kernels.cu", "pair_kernels.cu", "frame_kernels.cu", "photo_kernels.cu", "smooth_kernels.cu", "pft_kernels.cu"]
+SOURCES = ["cabi.cu", "warp_kernels.cu", "ssim_kernels.cu", "pair_kernels.cu", "pair_fast_kernels.cu", "frame_kernels.cu", "photo_kernels.cu", "smooth_kernels.cu", "pft_kernels.cu"]
 
 
 def digest():

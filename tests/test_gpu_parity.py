@@ -696,3 +696,93 @@ def test_graph_replay_follows_changed_intrinsics():
     out = O.compute_loss(goldens.FULL_CFG, fr["sources"], fr["target"], [fr["poses"], fr["poses_inv"]],
                          [[d] for d in fresh], K2)
     assert abs(float(got) - float(out["total"])) <= 1e-5 * abs(float(out["total"]))
+
+
+# ------------------------------------------------- "fast" SSIM arithmetic (TCSFM_ARITH_FAST, csrc/pair_fast_kernels.cu)
+@pytest.fixture()
+def fast_arith():
+    ops.set_arithmetic("fast")
+    yield
+    ops.set_arithmetic("exact")
+
+
+FAST_SHAPES = [(8, 192, 640, 0.01, synth.KITTI_DEPTH_RANGE, 2),       # BASELINE config 2
+               (16, 256, 320, 0.04, synth.SCANNET_DEPTH_RANGE, 1),    # config 3
+               (2, 376, 1242, 0.02, synth.KITTI_DEPTH_RANGE, 2),      # config 5 resolution
+               (4, 256, 448, 0.02, synth.SCANNET_DEPTH_RANGE, 1),
+               (3, 51, 77, 0.08, synth.KITTI_DEPTH_RANGE, 3),         # odd sizes, three sources
+               (1, 192, 640, 0.02, synth.KITTI_DEPTH_RANGE, 2)]       # batch 1: the non-fused cuBLAS flavour
+
+
+@pytest.mark.parametrize("shape", FAST_SHAPES)
+@pytest.mark.parametrize("tag", ["train", "full"])
+def test_fast_compute_loss_vs_eager_cuda(fast_arith, shape, tag):
+    """North-star tolerances for the fast flavour: every loss term within 1e-5, gradients within 1e-4 (rel-L2) of the
+    reference's eager CUDA path."""
+    b, h, w, yaw, rng, n_src = shape
+    fr = synth.make_frames(b, h, w, n_src=n_src, seed=21, yaw=yaw, depth_range=rng, device=DEV,
+                           intrinsics=synth.scaled_intrinsics(h, w))
+    cfg = dict(goldens.LOSS_CFGS[tag], min_depth=rng[0], max_depth=rng[1])
+    res = []
+    for impl in ("oracle", "cuda"):
+        disps = [leaf(d) for d in fr["disps"]]
+        poses, poses_inv = [leaf(p) for p in fr["poses"]], [leaf(p) for p in fr["poses_inv"]]
+        dl = [[d] for d in disps]
+        if impl == "oracle":
+            out = O.compute_loss(cfg, fr["sources"], fr["target"], [poses, poses_inv], dl, fr["K"])
+        else:
+            out = losses.Compute_Loss(cfg)(fr["sources"], fr["target"], [poses, poses_inv], dl, fr["K"])
+        out["total"].sum().backward()
+        res.append((out, disps, poses, poses_inv))
+    (ro, rd, rp, rpi), (go, gd, gp, gpi) = res
+    for k in ("l_reconstruct_inverse", "l_reconstruct_forward", "l_depth", "total"):
+        a, bb = float(go[k].detach()), float(ro[k].detach())
+        assert abs(a - bb) <= 1e-5 * max(abs(bb), 1e-12), (k, a, bb)
+
+    def grad(t):
+        return t.grad if t.grad is not None else torch.zeros_like(t)
+    for j in range(1 + n_src):
+        assert rel_l2(grad(gd[j]), grad(rd[j])) < 1e-4, ("disp", j, rel_l2(grad(gd[j]), grad(rd[j])))
+    for j in range(n_src):
+        assert rel_l2(grad(gp[j]), grad(rp[j])) < 1e-4, ("pose", j, rel_l2(grad(gp[j]), grad(rp[j])))
+        assert rel_l2(grad(gpi[j]), grad(rpi[j])) < 1e-4, ("pose_inv", j, rel_l2(grad(gpi[j]), grad(rpi[j])))
+
+
+@pytest.mark.parametrize("shape", FAST_SHAPES)
+def test_fast_pair_masks_bit_exact_vs_eager_cuda(fast_arith, shape):
+    """The fast flavour keeps geometry, warp, L1 and the auto-mask comparison bit-exact: valid / auto masks identical
+    to eager PyTorch on the same GPU; diff_img at the reference's own fp32 noise floor."""
+    b, h, w, yaw, rng, _ = shape
+    fr = frames(b, h, w, yaw, rng, seed=5)
+    for tag in ("train", "full", "noauto"):
+        cfg = goldens.PAIR_CFGS[tag]
+        for tgt, ref, td, rd, pose in ((fr["target"], fr["sources"][0], fr["depths"][0], fr["depths"][1], -fr["poses"][0]),
+                                       (fr["sources"][1], fr["target"], fr["depths"][2], fr["depths"][0], -fr["poses_inv"][1])):
+            _, _, rdiff, rmask, _ = O.pairwise_loss(cfg, tgt, ref, td, rd, pose, fr["K"])
+            _, _, gdiff, gmask, _ = losses.Compute_Loss(cfg).compute_pairwise_loss(tgt, ref, td, rd, pose, fr["K"], 0)
+            assert torch.equal(gmask, rmask), (tag, int((gmask != rmask).sum()))
+            assert rel_l2(gdiff, rdiff) < 5e-5, (tag, rel_l2(gdiff, rdiff))
+
+
+def test_fast_randomised_sweep_vs_eager_cuda(fast_arith):
+    """Random shapes, skewed intrinsics, depth scales and poses (incl. points behind the camera) through the fast
+    flavour: masks bit-exact, loss 1e-5, gradients 1e-4."""
+    gen = torch.Generator().manual_seed(1234)
+    for it in range(12):
+        b = int(torch.randint(1, 5, (1,), generator=gen))
+        h = int(torch.randint(20, 200, (1,), generator=gen))
+        w = int(torch.randint(20, 300, (1,), generator=gen))
+        fr = frames(b, h, w, float(torch.rand(1, generator=gen)) * 0.1, synth.KITTI_DEPTH_RANGE, seed=100 + it)
+        fr["K"][:, 0, 1] = float(torch.rand(1, generator=gen)) * 2.0          # skew
+        cfg = goldens.FULL_CFG
+        res = []
+        for impl in ("oracle", "cuda"):
+            disps = [leaf(d) for d in fr["disps"]]
+            dl = [[d] for d in disps]
+            args = (fr["sources"], fr["target"], [fr["poses"], fr["poses_inv"]], dl, fr["K"])
+            out = O.compute_loss(cfg, *args) if impl == "oracle" else losses.Compute_Loss(cfg)(*args)
+            out["total"].sum().backward()
+            res.append((float(out["total"].detach()), [d.grad for d in disps]))
+        assert abs(res[1][0] - res[0][0]) <= 1e-5 * abs(res[0][0]), (it, b, h, w, res[1][0], res[0][0])
+        for j in range(3):
+            assert rel_l2(res[1][1][j], res[0][1][j]) < 1e-4, (it, b, h, w, j, rel_l2(res[1][1][j], res[0][1][j]))

@@ -2,7 +2,7 @@
 package loader and by the test-only emulator binding)."""
 import ctypes as C
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 ARITH_CPU = 1 << 0
 AUTO_MASK = 1 << 1
@@ -11,6 +11,7 @@ DEPTH_MASK = 1 << 3
 DEPTH_CONSIST = 1 << 4
 SHARED_GRADS = 1 << 5
 ARITH_BMM_NOFMA = 1 << 6
+ARITH_FAST = 1 << 7
 
 PFT_ARGMIN = 1 << 0
 PFT_AUTOMASK = 1 << 1
@@ -55,6 +56,7 @@ SIGNATURES = {
     "tcsfm_pft_reduce_bwd": (C.c_int, [_fp] * 8 + [C.c_int, C.c_int, _i64, C.c_int, C.c_float, _fp, _fp,
                                                     _fp, _fp, _fp, _fp, C.c_void_p]),
     "tcsfm_pair_coef_planes": (C.c_int, []),
+    "tcsfm_pair_ws_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "tcsfm_pair_loss_fwd": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "tcsfm_pair_loss_bwd": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int,

@@ -208,7 +208,8 @@ def pair_loss_fwd(lib, batch, w_l1, w_ssim, flags, want_diff=True, want_grad=Tru
     diff = torch.empty((g, b, 1, h, w), dtype=torch.float32, device=dev) if want_diff else None
     mask = torch.empty((g, b, 1, h, w), dtype=torch.float32, device=dev)
     sums = torch.empty((g, 4), dtype=torch.float32, device=dev)
-    coef = torch.empty((g, b, lib.tcsfm_pair_coef_planes(), h, w), dtype=torch.float32, device=dev) if want_grad else None
+    # workspace the forward leaves for the backward (layout private to the arithmetic flavour in `flags`)
+    coef = torch.empty((g, b, lib.tcsfm_pair_ws_floats(h, w, flags)), dtype=torch.float32, device=dev) if want_grad else None
     for i in range(g):
         a = batch.arr[i]
         a.diff_img = _ptr(diff[i]) if want_diff else None

@@ -13,7 +13,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libtcsfm_b200.so")
-SOURCES = ["cabi.cu", "warp_kernels.cu", "ssim_kernels.cu", "pair_kernels.cu", "frame_kernels.cu", "photo_kernels.cu", "smooth_kernels.cu", "pft_kernels.cu"]
+SOURCES = ["cabi.cu", "warp_kernels.cu", "ssim_kernels.cu", "pair_kernels.cu", "pair_fast_kernels.cu", "frame_kernels.cu", "photo_kernels.cu", "smooth_kernels.cu", "pft_kernels.cu"]
 HEADERS = ["common.cuh", "tcsfm_math.cuh", "tile.cuh", os.path.join("..", "..", "include", "tcsfm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               # parity-critical arithmetic uses explicit *_rn intrinsics (never contracted);

@@ -65,6 +65,27 @@ __device__ __forceinline__ void store_global(float* p, float v) {
 #endif
 }
 
+// Workspace stores: written once, read once by the backward much later -- the evict-first hint keeps them from
+// pushing the images / depths (which the other pair groups of the frame are about to gather) out of L2.
+__device__ __forceinline__ void store_streaming(float* p, float v) {
+#if defined(TCSFM_HOST_EMU)
+    *p = v;
+#elif defined(TCSFM_WS_NO_STREAMING)
+    asm volatile("st.global.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+#else
+    asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void store_streaming2(float* p, float2 v) {
+#if defined(TCSFM_HOST_EMU)
+    p[0] = v.x; p[1] = v.y;
+#elif defined(TCSFM_WS_NO_STREAMING)
+    asm volatile("st.global.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+#else
+    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+#endif
+}
+
 // One 4-byte cp.async global -> shared; `live == false` writes a zero instead of reading
 // `src` (the ignore-src form: a single LDGSTS with a predicate operand, where the
 // cuda_pipeline.h helper with a run-time zfill emits two predicated copies).
@@ -75,6 +96,18 @@ __device__ __forceinline__ void async_copy4(float* smem_dst, const float* src, b
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t"
                  "cp.async.ca.shared.global [%0], [%1], 4, p;\n\t}"
+                 :: "r"(dst), "l"(src), "r"((unsigned)live) : "memory");
+#endif
+}
+
+// Two consecutive floats (both addresses 8-byte aligned).
+__device__ __forceinline__ void async_copy8(float* smem_dst, const float* src, bool live) {
+#ifdef TCSFM_HOST_EMU
+    for (int i = 0; i < 2; ++i) smem_dst[i] = live ? src[i] : 0.f;
+#else
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t"
+                 "cp.async.ca.shared.global [%0], [%1], 8, p;\n\t}"
                  :: "r"(dst), "l"(src), "r"((unsigned)live) : "memory");
 #endif
 }

@@ -255,9 +255,9 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
                 const float gq = (depth_mask ? (1.0f - own_dd[k]) : 1.0f) * A.third * L.w_ssim;
                 const SsimCoef kf = ssim_coef(s, t, gq);            // x = target, y = warped
                 const int o = (3 * ch) * n + gy * W + gx;
-                store_global(coef_base + o, kf.Ay);
-                store_global(coef_base + (o + n), kf.B);
-                store_global(coef_base + (o + 2 * n), kf.Cc);
+                store_streaming(coef_base + o, kf.Ay);
+                store_streaming(coef_base + (o + n), kf.B);
+                store_streaming(coef_base + (o + 2 * n), kf.Cc);
             }
         }
     }
@@ -273,7 +273,7 @@ pair_fwd_kernel(const __grid_constant__ PairLaunch L) {
             const int64_t o = (int64_t)b * n + gy * W + gx;
             if (g.diff_img) g.diff_img[o] = diff;
             if (g.mask) g.mask[o] = own_mask[k];
-            if (coef_base) store_global(coef_base + (9 * n + gy * W + gx), diff0);
+            if (coef_base) store_streaming(coef_base + (9 * n + gy * W + gx), diff0);
             part[0] += diff * own_mask[k];
             part[1] += own_mask[k];
             if (depth_consist) part[2] += own_dd[k] * own_mask[k];
@@ -651,9 +651,16 @@ using namespace tcsfm;
 
 extern "C" int tcsfm_pair_coef_planes(void) { return kCoefPlanes; }
 
+// the tolerance-level SSIM arithmetic: csrc/pair_fast_kernels.cu
+int tcsfm_pair_fast_fwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
+                        float w_l1, float w_ssim, int flags, void* stream);
+int tcsfm_pair_fast_bwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
+                        float w_l1, float w_ssim, int flags, void* stream);
+
 extern "C" int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
                                    float w_l1, float w_ssim, int flags, void* stream) {
     if (!groups || n_groups <= 0) { set_error("tcsfm_pair_loss_fwd: no groups"); return 1; }
+    if (flags & TCSFM_ARITH_FAST) return tcsfm_pair_fast_fwd(groups, n_groups, B, H, W, w_l1, w_ssim, flags, stream);
     const size_t smem = 3 * Tile<1>::kCells * sizeof(float2);
     const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
     for (int base = 0; base < n_groups; base += kMaxGroups) {
@@ -678,6 +685,7 @@ extern "C" int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
 extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
                                    float w_l1, float w_ssim, int flags, void* stream) {
     if (!groups || n_groups <= 0) { set_error("tcsfm_pair_loss_bwd: no groups"); return 1; }
+    if (flags & TCSFM_ARITH_FAST) return tcsfm_pair_fast_bwd(groups, n_groups, B, H, W, w_l1, w_ssim, flags, stream);
     const size_t smem = kBwdSmemBytes;
     const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
     for (int base = 0; base < n_groups; base += kMaxGroups) {

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi, ops
-from .stn import inverse_intrinsics, inverse_warp2, pose_vec2mat
+from .stn import inverse_intrinsics, inverse_intrinsics_forked, inverse_warp2, pose_vec2mat
 
 
 class SSIM_Loss(nn.Module):
@@ -125,7 +125,7 @@ class Compute_Loss(nn.modules.Module):
                 # disparities [B,1,h,w] of one scale share a resolution (possibly lower than the images')
                 and all(s[k].dim() == 4 and s[k].shape == specs[0][2].shape for s in specs for k in (2, 3)))
 
-    def _frame_terms(self, specs, roles, intrinsics, kinv):
+    def _frame_terms(self, specs, roles, intrinsics, kinv, kinv_ready=None):
         """All pair evaluations of one scale plus disp_to_depth, the pose algebra and the
         min-reprojection / mean-on-mask reductions as one fused autograd node.  `specs` are
         (tgt_img, ref_img, tgt_disp, ref_disp, pose) with the disparities at their own pyramid
@@ -148,7 +148,7 @@ class Compute_Loss(nn.modules.Module):
                 "flags": _pair_flags(self.config), "w_inverse": 0.3,
                 "w_depth": float(self.l_depth_consist_weight) if want_depth else 0.0,
                 "min_depth": self.config['min_depth'], "max_depth": self.config['max_depth'],
-                "n_img": len(images), "groups": groups}
+                "n_img": len(images), "groups": groups, "kinv_ready": kinv_ready}
         # check_sizes accepts [B,8] pose vectors (models/stn.py:252); only the first six enter the warp
         poses = [s[4] if s[4].shape[1] == 6 else s[4][:, 0:6] for s in specs]
         return ops.FrameLossFn.apply(meta, kinv, intrinsics, *poses, *images, *disps)
@@ -165,7 +165,7 @@ class Compute_Loss(nn.modules.Module):
         # the kernel's sum is the whole `total` only when this call evaluates exactly one scale and divides
         # by one (the reference loops over every entry of `disparity` whatever num_scales says, losses.py:84,136)
         single_scale = len(disparity[0]) == 1 and self.num_scales == 1
-        kinv = None
+        kinv, kinv_ready = None, None
         disparity, source_disparities = disparity[0], disparity[1:]
         poses, poses_inv = poses[0], poses[1]
         _, _, h, w = target_img.size()
@@ -200,9 +200,10 @@ class Compute_Loss(nn.modules.Module):
                     roles.append('fwd')
                 if self._can_fuse_frame(specs, intrinsics):
                     self._refuse_image_grads(specs)
-                    if kinv is None:
-                        kinv = inverse_intrinsics(intrinsics)            # models/stn.py:257, once per call
-                    terms, total = self._frame_terms(specs, roles, intrinsics, kinv)
+                    if kinv is None:                                     # models/stn.py:257, once per call, on a side stream
+                        kinv, kinv_ready = inverse_intrinsics_forked(intrinsics)
+                    terms, total = self._frame_terms(specs, roles, intrinsics, kinv, kinv_ready)
+                    kinv_ready = None                                    # the main stream has joined
                     fresh = scale == 0          # 0 + x == x: skip the add into the zero tensor
                     for i, key in enumerate(keys[:3]):
                         losses[key] = terms[i:i + 1] if fresh else losses[key] + terms[i:i + 1]

@@ -20,7 +20,7 @@ ARITH_FLAGS = 0
 # diff_img / SSIM maps); "fast" (when the library provides it) keeps geometry, warp, L1 and every mask bit-exact
 # and evaluates the 3x3 SSIM statistics at tolerance level (loss <= 1e-5, gradients <= 1e-4 of the reference).
 PAIR_ARITHMETIC = "exact"
-PAIR_ARITHMETICS = ("exact",)
+PAIR_ARITHMETICS = ("exact", "fast")
 
 
 def set_arithmetic(mode):
@@ -37,6 +37,14 @@ def arith_flags(batch, height, width):
     flags = ARITH_FLAGS
     if not (flags & _cabi.ARITH_CPU) and batch == 1 and 9 * height * width <= (1 << 21):
         flags |= _cabi.ARITH_BMM_NOFMA
+    return flags
+
+
+def pair_flags(batch, height, width):
+    """arith_flags plus the SSIM arithmetic selected for the fused pair loss."""
+    flags = arith_flags(batch, height, width)
+    if PAIR_ARITHMETIC == "fast":
+        flags |= _cabi.ARITH_FAST
     return flags
 
 
@@ -172,7 +180,7 @@ class PairLossFn(torch.autograd.Function):
             t = tensors[4 * i:4 * i + 4]
             groups.append({"tgt_img": t[0], "ref_img": t[1], "tgt_depth": t[2], "ref_depth": t[3],
                            "kinv": kinv, "proj": proj[i * b:(i + 1) * b]})
-        flags = flags | arith_flags(b, tensors[0].shape[2], tensors[0].shape[3])
+        flags = flags | pair_flags(b, tensors[0].shape[2], tensors[0].shape[3])
         with _guard(kinv):
             batch = _raw.PairBatch(groups)
             want_grad = any(ctx.needs_input_grad)
@@ -251,7 +259,7 @@ class FrameLossFn(torch.autograd.Function):
         groups = meta["groups"]
         g, b = len(groups), K.shape[0]
         poses_in, images, disps = tensors[:g], tensors[g:g + meta["n_img"]], tensors[g + meta["n_img"]:]
-        flags = meta["flags"] | arith_flags(b, images[0].shape[2], images[0].shape[3])
+        flags = meta["flags"] | pair_flags(b, images[0].shape[2], images[0].shape[3])
         min_disp, max_disp = 1 / meta["max_depth"], 1 / meta["min_depth"]      # learning_helpers.py:82-83
         with _guard(K):
             kinv = kinv.contiguous()
@@ -267,6 +275,8 @@ class FrameLossFn(torch.autograd.Function):
                       "kinv": kinv, "proj": proj[i * b:(i + 1) * b]} for i, (_, ti, ri, td, rd) in enumerate(groups)]
             batch = _raw.PairBatch(specs)
             want_grad = any(ctx.needs_input_grad)
+            if meta.get("kinv_ready") is not None:         # K^-1 was forked onto a side stream (stn.inverse_intrinsics_forked)
+                torch.cuda.current_stream(K.device).wait_event(meta["kinv_ready"])
             diff, mask, sums, coef = _raw.pair_loss_fwd(lib(), batch, meta["w_l1"], meta["w_ssim"], flags, want_grad=want_grad)
             fwd_idx = [i for i, grp in enumerate(groups) if grp[0] == 1]
             step = fwd_idx[1] - fwd_idx[0] if len(fwd_idx) > 1 else 1

@@ -85,6 +85,30 @@ def inverse_intrinsics(intrinsics):
     return torch.linalg.inv_ex(intrinsics.detach())[0]
 
 
+_SIDE_STREAMS = {}
+
+
+def inverse_intrinsics_forked(intrinsics):
+    """K^-1 as above, computed on a side stream so that the handful of tiny batched-LU launches overlap the
+    launches that do not need it (disp -> depth, pose -> K[R|t]).  Returns (kinv, event): the consumer's
+    stream waits for `event` (None on the CPU) before the first kernel that reads kinv.  The fork / join is
+    plain event traffic, so it is captured into CUDA graphs as a parallel branch."""
+    if not intrinsics.is_cuda:
+        return inverse_intrinsics(intrinsics), None
+    dev = intrinsics.device
+    main = torch.cuda.current_stream(dev)
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        kinv = inverse_intrinsics(intrinsics).contiguous()     # (torch.inverse returns K^-1 column-major)
+        event = torch.cuda.Event()
+        event.record(side)
+    kinv.record_stream(main)
+    return kinv, event
+
+
 def projection_matrices(pose, intrinsics, kinv=None):
     """(K^-1, K @ [R|t]) as models/stn.py:257-262 forms them.  On the GPU the 25-kernel euler/bmm
     chain is one fused launch that reproduces it bit for bit (csrc/frame_kernels.cu), including
