@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 9
+#define TCSFM_ABI_VERSION 10
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -237,6 +237,17 @@ int tcsfm_disp_upsample_to_depth_bwd(const float* const* g_depth, const float* c
 
 /* out_sum[0] = sum_i min_j base[j*stride + i], j < count, i < n  (losses.py:129-131). */
 int tcsfm_min_reduce(const float* base, int64_t stride, int count, int64_t n, float* out_sum, void* stream);
+
+/* Near-ties of that minimum: the same sum, plus (tie_list [capacity], tie_count [1], both device int32) the flat
+ * indices i whose two smallest candidates differ by less than `band` (or involve a NaN).  tcsfm_pair_tie_resolve
+ * then overwrites diff_img[i] of every listed group with the value the exact arithmetic gives, so that the arg-min
+ * routing of the backward (torch.min, first index on ties) is the reference's even when the maps were produced by
+ * TCSFM_ARITH_FAST.  groups: the competing (forward) groups in candidate order, forward fields filled. */
+int tcsfm_min_reduce_ties(const float* base, int64_t stride, int count, int64_t n, float* out_sum, float band,
+                          int* tie_list, int* tie_count, int capacity, void* stream);
+int tcsfm_pair_tie_resolve(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
+                           float w_l1, float w_ssim, int flags, const int* tie_list, const int* tie_count, int capacity,
+                           void* stream);
 
 typedef struct tcsfm_frame_cfg {
     int32_t n_groups;       /* pair groups of the launch, in the reference's evaluation order      */

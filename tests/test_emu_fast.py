@@ -142,3 +142,47 @@ def test_fast_three_sources_and_multi_scale(emu_fast):
     assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[1][0])
     for a, b in zip(res[0][1], res[1][1]):
         assert rel_l2(a, b) < 1e-4, rel_l2(a, b)
+
+
+def test_tie_resolver_restores_the_reference_routing():
+    """After tcsfm_min_reduce_ties + tcsfm_pair_tie_resolve the fast flavour's forward maps hold the exact kernels'
+    values at every near-tie pixel, and the per-pixel arg-min over the sources is the exact arithmetic's everywhere."""
+    fr = synth.make_frames(2, 40, 70, seed=4)
+    # make the two sources nearly identical inside a patch so that near-ties are plentiful there (the list holds
+    # max(1024, n/8) entries; a map made of ties only would overflow it, which is allowed but not what is tested here)
+    patch = torch.zeros_like(fr["sources"][0])
+    patch[:, :, 8:18, 10:25] = 1.0
+    fr["sources"][1] = torch.where(patch > 0, (fr["sources"][0] + 1e-4 * torch.randn_like(fr["sources"][0])).clamp(0, 1),
+                                   (fr["sources"][0] * 0.5 + 0.2))
+    fr["depths"][2] = fr["depths"][1].clone()
+    fr["poses"][1] = fr["poses"][0].clone()
+    cfg = goldens.FULL_CFG
+    K = fr["K"]
+
+    def forward(flags):
+        groups = []
+        for j in range(2):
+            kinv, proj = stn.projection_matrices(-fr["poses"][j], K)
+            groups.append({"tgt_img": fr["target"], "ref_img": fr["sources"][j], "tgt_depth": fr["depths"][0],
+                           "ref_depth": fr["depths"][1 + j], "kinv": kinv, "proj": proj})
+        batch = _raw.PairBatch(groups)
+        diff, mask, sums, coef = _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, flags)
+        return batch, diff
+
+    exact_flags = cfg_flags(cfg) & ~_cabi.ARITH_FAST
+    _, d_exact = forward(exact_flags)
+    batch, d_fast = forward(cfg_flags(cfg))
+    n_px = d_fast[0].numel()
+    before = d_fast.clone()
+    min_sum, tie_list, tie_count = _raw.min_reduce_ties(emu(), d_fast[0], n_px, 2, n_px)
+    n_ties = int(tie_count)
+    assert 0 < n_ties <= tie_list.numel()
+    _raw.pair_tie_resolve(emu(), batch, [0, 1], 0.15, 0.85, cfg_flags(cfg), tie_list, tie_count)
+    idx = tie_list[:n_ties].long()
+    for j in range(2):
+        assert torch.equal(d_fast[j].flatten()[idx], d_exact[j].flatten()[idx])          # exact values at the ties
+        untouched = torch.ones(n_px, dtype=torch.bool)
+        untouched[idx] = False
+        assert torch.equal(d_fast[j].flatten()[untouched], before[j].flatten()[untouched])
+    assert torch.equal(torch.min(d_fast.reshape(2, -1), 0)[1], torch.min(d_exact.reshape(2, -1), 0)[1])
+    assert abs(float(min_sum) - float(torch.min(before.reshape(2, -1), 0)[0].sum())) < 1e-3

@@ -283,6 +283,33 @@ def min_reduce(lib, first, stride, count, n):
     return out
 
 
+TIE_BAND = 5e-4     # |second smallest - smallest| below which the per-pixel min is re-decided with the exact arithmetic
+
+
+def min_reduce_ties(lib, first, stride, count, n):
+    """min_reduce plus the list of near-tie pixels: returns (sum [1], tie_list int32 [cap], tie_count int32 [1])."""
+    out = torch.empty((1,), dtype=torch.float32, device=first.device)
+    cap = max(1024, n // 8)
+    tie_list = torch.empty((cap,), dtype=torch.int32, device=first.device)
+    tie_count = torch.empty((1,), dtype=torch.int32, device=first.device)
+    with _timing.launch("min_reduce", first.is_cuda):
+        rc = lib.tcsfm_min_reduce_ties(_ptr(first), stride, count, n, _ptr(out), TIE_BAND, _ptr(tie_list), _ptr(tie_count), cap,
+                                       _stream(first))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return out, tie_list, tie_count
+
+
+def pair_tie_resolve(lib, batch, group_ids, w_l1, w_ssim, flags, tie_list, tie_count):
+    """Overwrites diff_img of the listed competing groups at the near-tie pixels with the exact arithmetic's value."""
+    sub = (PairGroup * len(group_ids))(*[batch.arr[i] for i in group_ids])
+    with _timing.launch("pair_tie_resolve", batch.device.type == "cuda"):
+        rc = lib.tcsfm_pair_tie_resolve(sub, len(group_ids), batch.b, batch.h, batch.w, w_l1, w_ssim, flags,
+                                        _ptr(tie_list), _ptr(tie_count), tie_list.numel(), batch.stream())
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+
+
 def make_frame_cfg(roles, w_inverse, w_depth, n_min_pixels):
     cfg = _cabi.FrameCfg()
     cfg.n_groups = len(roles)

@@ -218,6 +218,32 @@ min_reduce_kernel(const float* __restrict__ base, int64_t stride, int count, int
     block_atomic_accumulate<1>(part, red, out, threadIdx.x, kReduceThreads);
 }
 
+// The same sum, plus the list of pixels whose two smallest candidates are closer than `band` (or involve a NaN): the
+// near-ties of the per-pixel min (losses.py:129-132) that the "fast" pair arithmetic re-evaluates exactly
+// (tcsfm_pair_tie_resolve) so that the arg-min routing of the backward stays the reference's.
+__global__ void __launch_bounds__(kReduceThreads)
+min_reduce_ties_kernel(const float* __restrict__ base, int64_t stride, int count, int64_t n, float* __restrict__ out,
+                       float band, int* __restrict__ tie_list, int* __restrict__ tie_count, int capacity) {
+    TCSFM_SHARED float red[kReduceThreads / 32];
+    float part[1] = {0.f};
+    for (int64_t i = (int64_t)blockIdx.x * kReduceThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kReduceThreads) {
+        float m = __ldg(base + i), second = INFINITY;
+        bool odd = m != m;
+        for (int j = 1; j < count; ++j) {
+            const float v = __ldg(base + j * stride + i);
+            odd = odd || v != v;
+            if (v < m) { second = m; m = v; }
+            else if (v < second) second = v;
+        }
+        part[0] += m;
+        if (count > 1 && (odd || !(second - m >= band))) {
+            const int at = atomicAdd(tie_count, 1);
+            if (at < capacity) tie_list[at] = (int)i;
+        }
+    }
+    block_atomic_accumulate<1>(part, red, out, threadIdx.x, kReduceThreads);
+}
+
 __global__ void frame_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ min_sum, tcsfm_frame_cfg cfg,
                                       float* __restrict__ out, float* __restrict__ total) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -252,6 +278,21 @@ __global__ void frame_bwd_prepare_kernel(const float* __restrict__ g_out, const 
 }  // namespace tcsfm
 
 using namespace tcsfm;
+
+extern "C" int tcsfm_min_reduce_ties(const float* base, int64_t stride, int count, int64_t n, float* out_sum, float band,
+                                     int* tie_list, int* tie_count, int capacity, void* stream) {
+    if (!base || !out_sum || !tie_list || !tie_count || count <= 0 || n <= 0 || capacity <= 0) {
+        set_error("tcsfm_min_reduce_ties: bad arguments"); return 1;
+    }
+    if (n >= ((int64_t)1 << 31)) { set_error("tcsfm_min_reduce_ties: more than 2^31 pixels"); return 1; }
+    cudaMemsetAsync(out_sum, 0, sizeof(float), (cudaStream_t)stream);
+    cudaMemsetAsync(tie_count, 0, sizeof(int), (cudaStream_t)stream);
+    const int64_t blocks = (n + kReduceThreads - 1) / kReduceThreads;
+    const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+    TCSFM_LAUNCH(min_reduce_ties_kernel, dim3(grid), dim3(kReduceThreads), 0, stream, base, stride, count, n, out_sum, band,
+                 tie_list, tie_count, capacity);
+    return check_launch("tcsfm_min_reduce_ties");
+}
 
 extern "C" int tcsfm_pose_proj_fwd(const float* pose, float sign, const float* K, int Bk, float* proj, int N, int flags,
                                    void* stream) {

@@ -617,6 +617,61 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     if (g.g_proj) block_atomic_accumulate<12>(acc, cs, g.g_proj + b * 12, threadIdx.x, kTileThreads);
 }
 
+// ---------------------------------------------------------------------------
+// exact re-evaluation of single pixels (the near-ties of the min-reprojection under the "fast" arithmetic)
+// ---------------------------------------------------------------------------
+// diff_img of one pixel exactly as pair_fwd_kernel computes it (every rounding step of eager PyTorch): the 3x3
+// window of (target, warped) per channel, avg_pool2d-ordered statistics, IEEE SSIM ratio, L1 blend, channel mean,
+// depth-consistency weight.
+template <int F>
+__device__ float exact_pair_diff(const tcsfm_pair_group& g, const PairLaunch& L, int b, int x, int y) {
+    const Arith& A = L.A;
+    const int H = A.H, W = A.W, n = H * W;
+    const Cam cam = load_cam(g.kinv, g.proj, b);
+    const PairCtx c = make_ctx(g, b, n);
+    const bool need_depth = (L.flags & TCSFM_DEPTH_MASK) != 0;
+    float t[3][9], w[3][9];
+    float dd = 0.f;
+    for (int i = 0; i < 9; ++i) {
+        const int ry = reflect1(y + i / 3 - 1, H), rx = reflect1(x + i % 3 - 1, W);
+        const int pix = ry * W + rx;
+        WarpPt p;
+        warp_point<F>(cam, A, rx, ry, __ldg(c.tdep + pix), p);
+        const TapIdx ti = make_taps(p, H, W);
+        for (int ch = 0; ch < 3; ++ch) {
+            w[ch][i] = blend(load_taps(c.ref, ch * c.ref_sc, ti, W), ti);
+            t[ch][i] = __ldg(c.tgt + (ch * c.tgt_sc + pix));
+        }
+        if (i == 4 && need_depth) dd = depth_inconsistency(p.Z, blend(load_taps(c.rdep, 0, ti, W), ti));
+    }
+    float esum = 0.f;
+    for (int ch = 0; ch < 3; ++ch) {
+        const SsimTerms tt = ssim_terms(ssim_stats(&t[ch][4], &w[ch][4], 3), L.C1, L.C2);
+        const float l1 = clamp01_nan(fabsf(__fsub_rn(t[ch][4], w[ch][4])));
+        const float e = __fadd_rn(__fmul_rn(l1, L.w_l1), __fmul_rn(clamp01_nan(tt.raw), L.w_ssim));
+        esum = (ch == 0) ? e : __fadd_rn(esum, e);
+    }
+    const float diff0 = mean3_of_sum<F>(esum, A);
+    return need_depth ? __fmul_rn(diff0, __fsub_rn(1.0f, dd)) : diff0;
+}
+
+// one thread per (listed pixel, competing group): overwrite the group's diff_img entry with the exact value
+template <int F>
+__global__ void __launch_bounds__(128)
+tie_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, const int* __restrict__ tie_list,
+                   const int* __restrict__ tie_count, int capacity) {
+    const int count = min(__ldg(tie_count), capacity);
+    const int task = blockIdx.x * 128 + threadIdx.x;
+    const int e = task / n_groups, j = task - e * n_groups;
+    if (e >= count) return;
+    const int n = L.A.H * L.A.W;
+    const int pix = __ldg(tie_list + e);
+    const int b = pix / n, r = pix - b * n;
+    const int y = r / L.A.W, x = r - y * L.A.W;
+    const tcsfm_pair_group& g = L.g[j];
+    g.diff_img[pix] = exact_pair_diff<F>(g, L, b, x, y);
+}
+
 static int fill_launch(PairLaunch& L, const tcsfm_pair_group* groups, int n, int B, int H, int W,
                        float w_l1, float w_ssim, int flags, const char* who, bool bwd) {
     if (B <= 0 || H < 2 || W < 2) { set_error("%s: bad shape B=%d H=%d W=%d", who, B, H, W); return 1; }
@@ -654,8 +709,6 @@ extern "C" int tcsfm_pair_coef_planes(void) { return kCoefPlanes; }
 // the tolerance-level SSIM arithmetic: csrc/pair_fast_kernels.cu
 int tcsfm_pair_fast_fwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
                         float w_l1, float w_ssim, int flags, void* stream);
-int tcsfm_pair_fast_bwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
-                        float w_l1, float w_ssim, int flags, void* stream);
 
 extern "C" int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
                                    float w_l1, float w_ssim, int flags, void* stream) {
@@ -685,7 +738,6 @@ extern "C" int tcsfm_pair_loss_fwd(const tcsfm_pair_group* groups, int n_groups,
 extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
                                    float w_l1, float w_ssim, int flags, void* stream) {
     if (!groups || n_groups <= 0) { set_error("tcsfm_pair_loss_bwd: no groups"); return 1; }
-    if (flags & TCSFM_ARITH_FAST) return tcsfm_pair_fast_bwd(groups, n_groups, B, H, W, w_l1, w_ssim, flags, stream);
     const size_t smem = kBwdSmemBytes;
     const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
     for (int base = 0; base < n_groups; base += kMaxGroups) {
@@ -717,4 +769,22 @@ extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
         if (int rc = check_launch("tcsfm_pair_loss_bwd")) return rc;
     }
     return 0;
+}
+
+/* The competing forward groups' diff_img entries at the listed pixels (tcsfm_min_reduce_ties) are recomputed with the
+ * exact arithmetic, whatever arithmetic produced the maps. */
+extern "C" int tcsfm_pair_tie_resolve(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
+                                      float w_l1, float w_ssim, int flags, const int* tie_list, const int* tie_count,
+                                      int capacity, void* stream) {
+    if (!groups || n_groups <= 0 || n_groups > kMaxGroups) { set_error("tcsfm_pair_tie_resolve: 1..%d groups", kMaxGroups); return 1; }
+    if (!tie_list || !tie_count || capacity <= 0) { set_error("tcsfm_pair_tie_resolve: null tie list"); return 1; }
+    PairLaunch L;
+    memset(&L, 0, sizeof(L));
+    if (int rc = fill_launch(L, groups, n_groups, B, H, W, w_l1, w_ssim, flags & ~TCSFM_ARITH_FAST, "tcsfm_pair_tie_resolve", false)) return rc;
+    for (int i = 0; i < n_groups; ++i)
+        if (!L.g[i].diff_img) { set_error("tcsfm_pair_tie_resolve: group %d has no diff_img", i); return 1; }
+    const int64_t tasks = (int64_t)capacity * n_groups;
+    dim3 grid((unsigned)((tasks + 127) / 128)), block(128);
+    TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(tie_resolve_kernel<F>, grid, block, 0, stream, L, n_groups, tie_list, tie_count, capacity));
+    return check_launch("tcsfm_pair_tie_resolve");
 }

@@ -284,7 +284,11 @@ class FrameLossFn(torch.autograd.Function):
                 raise ValueError("forward groups must be evenly spaced")
             n_px = diff[0].numel()
             min_sum = None
-            if fwd_idx:
+            if fwd_idx and (flags & _cabi.ARITH_FAST) and len(fwd_idx) > 1:
+                # tolerance-level diff values: the near-ties of the per-pixel min are re-decided with the exact arithmetic
+                min_sum, tie_list, tie_count = _raw.min_reduce_ties(lib(), diff[fwd_idx[0]], step * n_px, len(fwd_idx), n_px)
+                _raw.pair_tie_resolve(lib(), batch, fwd_idx, meta["w_l1"], meta["w_ssim"], flags, tie_list, tie_count)
+            elif fwd_idx:
                 min_sum = _raw.min_reduce(lib(), diff[fwd_idx[0]], step * n_px, len(fwd_idx), n_px)
             cfg = _raw.make_frame_cfg([grp[0] for grp in groups], meta["w_inverse"], meta["w_depth"], n_px)
             # two separate tensors (not views of one buffer): callers may add to `total` in place
