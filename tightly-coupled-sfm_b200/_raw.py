@@ -283,13 +283,13 @@ def min_reduce(lib, first, stride, count, n):
     return out
 
 
-TIE_BAND = 5e-4     # |second smallest - smallest| below which the per-pixel min is re-decided with the exact arithmetic
+TIE_BAND = 2e-4     # |second smallest - smallest| below which the per-pixel min is re-decided with the exact arithmetic
 
 
 def min_reduce_ties(lib, first, stride, count, n):
     """min_reduce plus the list of near-tie pixels: returns (sum [1], tie_list int32 [cap], tie_count int32 [1])."""
     out = torch.empty((1,), dtype=torch.float32, device=first.device)
-    cap = max(1024, n // 8)
+    cap = max(1024, n // 16)
     tie_list = torch.empty((cap,), dtype=torch.int32, device=first.device)
     tie_count = torch.empty((1,), dtype=torch.int32, device=first.device)
     with _timing.launch("min_reduce", first.is_cuda):

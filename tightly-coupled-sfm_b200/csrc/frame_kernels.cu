@@ -221,10 +221,16 @@ min_reduce_kernel(const float* __restrict__ base, int64_t stride, int count, int
 // The same sum, plus the list of pixels whose two smallest candidates are closer than `band` (or involve a NaN): the
 // near-ties of the per-pixel min (losses.py:129-132) that the "fast" pair arithmetic re-evaluates exactly
 // (tcsfm_pair_tie_resolve) so that the arg-min routing of the backward stays the reference's.
+constexpr int kTieBuf = 1024;       // near-ties a block collects in shared memory before it reserves list space
+
 __global__ void __launch_bounds__(kReduceThreads)
 min_reduce_ties_kernel(const float* __restrict__ base, int64_t stride, int count, int64_t n, float* __restrict__ out,
                        float band, int* __restrict__ tie_list, int* __restrict__ tie_count, int capacity) {
     TCSFM_SHARED float red[kReduceThreads / 32];
+    TCSFM_SHARED int buf[kTieBuf];
+    TCSFM_SHARED int n_buf, list_at;
+    if (threadIdx.x == 0) n_buf = 0;
+    __syncthreads();
     float part[1] = {0.f};
     for (int64_t i = (int64_t)blockIdx.x * kReduceThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kReduceThreads) {
         float m = __ldg(base + i), second = INFINITY;
@@ -237,10 +243,20 @@ min_reduce_ties_kernel(const float* __restrict__ base, int64_t stride, int count
         }
         part[0] += m;
         if (count > 1 && (odd || !(second - m >= band))) {
-            const int at = atomicAdd(tie_count, 1);
-            if (at < capacity) tie_list[at] = (int)i;
+            const int at = atomicAdd(&n_buf, 1);                  // shared-memory counter: one global atomic per block below
+            if (at < kTieBuf) buf[at] = (int)i;
+            else {                                                // (a block with more than kTieBuf ties: straight to the list)
+                const int g_at = atomicAdd(tie_count, 1);
+                if (g_at < capacity) tie_list[g_at] = (int)i;
+            }
         }
     }
+    __syncthreads();
+    const int mine = n_buf < kTieBuf ? n_buf : kTieBuf;
+    if (threadIdx.x == 0) list_at = mine ? atomicAdd(tie_count, mine) : 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < mine; k += kReduceThreads)
+        if (list_at + k < capacity) tie_list[list_at + k] = buf[k];
     block_atomic_accumulate<1>(part, red, out, threadIdx.x, kReduceThreads);
 }
 

@@ -630,24 +630,41 @@ __device__ float exact_pair_diff(const tcsfm_pair_group& g, const PairLaunch& L,
     const Cam cam = load_cam(g.kinv, g.proj, b);
     const PairCtx c = make_ctx(g, b, n);
     const bool need_depth = (L.flags & TCSFM_DEPTH_MASK) != 0;
-    float t[3][9], w[3][9];
+    // the five avg_pool2d sums per channel accumulate row-major over the window, exactly like ssim_stats
+    float sx[3], sy[3], sxx[3], syy[3], sxy[3], tc[3], wc[3];
     float dd = 0.f;
+#pragma unroll 1
     for (int i = 0; i < 9; ++i) {
         const int ry = reflect1(y + i / 3 - 1, H), rx = reflect1(x + i % 3 - 1, W);
         const int pix = ry * W + rx;
         WarpPt p;
         warp_point<F>(cam, A, rx, ry, __ldg(c.tdep + pix), p);
         const TapIdx ti = make_taps(p, H, W);
+#pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-            w[ch][i] = blend(load_taps(c.ref, ch * c.ref_sc, ti, W), ti);
-            t[ch][i] = __ldg(c.tgt + (ch * c.tgt_sc + pix));
+            const float w = blend(load_taps(c.ref, ch * c.ref_sc, ti, W), ti);
+            const float t = __ldg(c.tgt + (ch * c.tgt_sc + pix));
+            if (i == 0) { sx[ch] = 0.f; sy[ch] = 0.f; sxx[ch] = 0.f; syy[ch] = 0.f; sxy[ch] = 0.f; }
+            sx[ch] = __fadd_rn(sx[ch], t);
+            sy[ch] = __fadd_rn(sy[ch], w);
+            sxx[ch] = __fadd_rn(sxx[ch], __fmul_rn(t, t));
+            syy[ch] = __fadd_rn(syy[ch], __fmul_rn(w, w));
+            sxy[ch] = __fadd_rn(sxy[ch], __fmul_rn(t, w));
+            if (i == 4) { tc[ch] = t; wc[ch] = w; }
         }
         if (i == 4 && need_depth) dd = depth_inconsistency(p.Z, blend(load_taps(c.rdep, 0, ti, W), ti));
     }
     float esum = 0.f;
+#pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        const SsimTerms tt = ssim_terms(ssim_stats(&t[ch][4], &w[ch][4], 3), L.C1, L.C2);
-        const float l1 = clamp01_nan(fabsf(__fsub_rn(t[ch][4], w[ch][4])));
+        SsimStats s;
+        s.mu_x = div9_exact(sx[ch]);
+        s.mu_y = div9_exact(sy[ch]);
+        s.sig_x = __fsub_rn(div9_exact(sxx[ch]), __fmul_rn(s.mu_x, s.mu_x));
+        s.sig_y = __fsub_rn(div9_exact(syy[ch]), __fmul_rn(s.mu_y, s.mu_y));
+        s.sig_xy = __fsub_rn(div9_exact(sxy[ch]), __fmul_rn(s.mu_x, s.mu_y));
+        const SsimTerms tt = ssim_terms(s, L.C1, L.C2);
+        const float l1 = clamp01_nan(fabsf(__fsub_rn(tc[ch], wc[ch])));
         const float e = __fadd_rn(__fmul_rn(l1, L.w_l1), __fmul_rn(clamp01_nan(tt.raw), L.w_ssim));
         esum = (ch == 0) ? e : __fadd_rn(esum, e);
     }

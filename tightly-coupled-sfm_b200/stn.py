@@ -205,3 +205,19 @@ def inverse_warp(img, depth, pose, intrinsics, rotation_mode='euler', padding_mo
     grid = cam2pixel(cam, proj[:, :, :3], proj[:, :, -1:], padding_mode)
     projected = F.grid_sample(img, grid, padding_mode=padding_mode)
     return projected, grid.abs().max(dim=-1)[0] <= 1
+
+
+def inverse_warp2_op(img, depth, ref_depth, pose, intrinsics, padding_mode='zeros'):
+    """inverse_warp2 through the `torch.library` registration (torch.ops.tcsfm.inverse_warp2): the spelling for
+    callers that trace with fake tensors / torch.compile; same results as inverse_warp2."""
+    from . import custom_ops  # noqa: F401  (registers the operators)
+    check_sizes(img, 'img', 'B3HW')
+    check_sizes(depth, 'depth', 'B1HW')
+    check_sizes(ref_depth, 'ref_depth', 'B1HW')
+    check_sizes(pose, 'pose', ['B6', 'B8'])
+    check_sizes(intrinsics, 'intrinsics', 'B33')
+    if padding_mode != 'zeros':
+        raise NotImplementedError("only padding_mode='zeros' is implemented")
+    kinv = inverse_intrinsics(intrinsics).contiguous()
+    proj = intrinsics @ pose_vec2mat(pose[:, 0:6])
+    return torch.ops.tcsfm.inverse_warp2(img, depth.contiguous(), ref_depth.contiguous(), kinv, proj.contiguous())
