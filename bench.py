@@ -288,6 +288,11 @@ def pft_measure(R, name, steps, warm, no_graph=False, sequence_frames=0):
     ksum = timer.summary()
     eager_window_ms = w0.elapsed_time(w1)
     hot_ms = sum(v["launches"] * v["avg_ms"] for v in ksum.values())
+    # the hot path proper: the same epoch body with the (out-of-scope) depth network replaced by leaf disparities --
+    # what is left besides the library's kernels is PyTorch glue (tools/profile_pft_hotpath.py)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import profile_pft_hotpath
+    proper = profile_pft_hotpath.run(3, wl["b"], wl["h"], wl["w"], wl["n_src"], wl["iterations"], dev, record=True)
     frames = wl["b"] * total_mbs
     h2d = sum(t.numel() * 4 for t in [host[0]["target"], host[0]["K"]] + host[0]["sources"])
     out = {"metric": "PFT frames/s", "value": frames / (ms / 1e3), "unit": "frames/s", "workload": wl["desc"],
@@ -300,7 +305,8 @@ def pft_measure(R, name, steps, warm, no_graph=False, sequence_frames=0):
                         "share_of_eager_window_device_time": hot_ms / eager_window_ms,
                         "note": "sum of the library launches' device time (CUDA events) over one eager window minibatch; "
                                 "the rest is the stand-in networks, Adam and PyTorch's own glue",
-                        "kernels": ksum}}
+                        "kernels": ksum,
+                        "without_depth_net": {k: v for k, v in proper.items() if k != "kernels"}}}
     if sequence_frames:
         mbs = shard.window_minibatches(sequence_frames, stride=2, minibatch=wl["b"])
         s_lo, s_hi = shard.shard_range(len(mbs), R.rank, R.world)

@@ -54,6 +54,7 @@ struct PairLaunch {
     float w_l1, w_ssim, C1, C2;
     int flags;
     int vec16;                       // backward: every coefficient row start is 16-byte aligned (W % 4 == 0, aligned base)
+    int B, n_groups;                 // backward: the persistent CTAs walk tasks = (group, batch element, tile)
 };
 
 struct PairCtx {
@@ -361,12 +362,37 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     using BT = BwdTile;
     TCSFM_DYN_SMEM(float, cs);                     // [9][BT::kCells] coefficients, [BT::kCells] upstream gradient
 
-    const tcsfm_pair_group& g = L.g[blockIdx.z];
+    // Persistent CTAs: the grid is one wave (SMs x resident CTAs); CTA i walks a contiguous range of the tasks
+    // (group, batch element, tile), tile fastest.  The twelve grad(K[R|t]) accumulators stay in registers across the
+    // tiles of one (group, batch element) and are block-reduced once when that changes (or at the end), instead of
+    // once per tile.
     const Arith& A = L.A;
     const int H = A.H, W = A.W, n = H * W;
-    const int b = blockIdx.y;
     const int tiles_x = (W + kTileW - 1) / kTileW;
-    const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+    const int tiles = tiles_x * ((H + kTileH - 1) / kTileH);
+    const int total = tiles * L.B * L.n_groups;
+    const int task_end = (int)(((int64_t)blockIdx.x + 1) * total / gridDim.x);
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+    int cur_gb = -1;
+    auto flush = [&](int gb) {                         // all threads; the tile doubles as reduction scratch
+        const int gi = gb / L.B, bb = gb - gi * L.B;
+        if (L.g[gi].g_proj) block_atomic_accumulate<12>(acc, cs, L.g[gi].g_proj + bb * 12, threadIdx.x, kTileThreads);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+    };
+#pragma unroll 1
+    for (int task = (int)((int64_t)blockIdx.x * total / gridDim.x); task < task_end; ++task) {
+    const int gb = task / tiles, tile = task - gb * tiles;
+    if (gb != cur_gb) {
+        if (cur_gb >= 0) flush(cur_gb);
+        cur_gb = gb;
+    }
+    const int group = gb / L.B;
+    const tcsfm_pair_group& g = L.g[group];
+    const int b = gb - group * L.B;
+    const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
     const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
     const Cam cam = load_cam(g.kinv, g.proj, b);
     const PairCtx c = make_ctx(g, b, n);
@@ -556,9 +582,6 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     }
 
     // ---- phase D, one own pixel at a time: L1 / depth adjoints and the geometry adjoint ----
-    float acc[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
 #pragma unroll kBwdDUnroll
     for (int k = 0; k < kPixPerThread; ++k) {
         const int gy = y0 + ty0 + k;
@@ -613,80 +636,97 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             }
         }
     }
-    __syncthreads();                                   // phase D is over everywhere: the tile doubles as reduction scratch
-    if (g.g_proj) block_atomic_accumulate<12>(acc, cs, g.g_proj + b * 12, threadIdx.x, kTileThreads);
+    __syncthreads();                                   // phase D is over everywhere: the tile is free for the next task
+    }
+    if (cur_gb >= 0) flush(cur_gb);
 }
 
 // ---------------------------------------------------------------------------
 // exact re-evaluation of single pixels (the near-ties of the min-reprojection under the "fast" arithmetic)
 // ---------------------------------------------------------------------------
-// diff_img of one pixel exactly as pair_fwd_kernel computes it (every rounding step of eager PyTorch): the 3x3
+// diff_img of single pixels exactly as pair_fwd_kernel computes it (every rounding step of eager PyTorch): the 3x3
 // window of (target, warped) per channel, avg_pool2d-ordered statistics, IEEE SSIM ratio, L1 blend, channel mean,
-// depth-consistency weight.
+// depth-consistency weight.  Sixteen lanes share one (listed pixel, competing group) task: lanes 0..8 warp one window
+// position each (one round of dependent gathers instead of nine), then every lane accumulates the window in
+// avg_pool2d's row-major order from the shuffled values and lane 0 overwrites the group's diff_img entry.
+constexpr int kTieTasksPerBlock = 8;
+
 template <int F>
-__device__ float exact_pair_diff(const tcsfm_pair_group& g, const PairLaunch& L, int b, int x, int y) {
+__global__ void __launch_bounds__(16 * kTieTasksPerBlock)
+tie_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, const int* __restrict__ tie_list,
+                   const int* __restrict__ tie_count, int capacity) {
+    const int n_tasks = min(__ldg(tie_count), capacity) * n_groups;
+    const int task0 = blockIdx.x * kTieTasksPerBlock;
+    if (task0 >= n_tasks) return;                          // the grid covers the list's capacity: most blocks are idle
+    const int sub = threadIdx.x & 15, task = task0 + (threadIdx.x >> 4);
+    const bool live = task < n_tasks;
+    const int e = live ? task / n_groups : 0, j = live ? task - e * n_groups : 0;
     const Arith& A = L.A;
     const int H = A.H, W = A.W, n = H * W;
+    const int pix = __ldg(tie_list + e);
+    const int b = pix / n, r = pix - b * n;
+    const int y = r / W, x = r - y * W;
+    const tcsfm_pair_group& g = L.g[j];
     const Cam cam = load_cam(g.kinv, g.proj, b);
     const PairCtx c = make_ctx(g, b, n);
     const bool need_depth = (L.flags & TCSFM_DEPTH_MASK) != 0;
-    // the five avg_pool2d sums per channel accumulate row-major over the window, exactly like ssim_stats
-    float sx[3], sy[3], sxx[3], syy[3], sxy[3], tc[3], wc[3];
-    float dd = 0.f;
-#pragma unroll 1
-    for (int i = 0; i < 9; ++i) {
-        const int ry = reflect1(y + i / 3 - 1, H), rx = reflect1(x + i % 3 - 1, W);
-        const int pix = ry * W + rx;
-        WarpPt p;
-        warp_point<F>(cam, A, rx, ry, __ldg(c.tdep + pix), p);
-        const TapIdx ti = make_taps(p, H, W);
+    const int i = sub < 9 ? sub : 4;                       // this lane's window position (idle lanes redo the centre)
+    const int ry = reflect1(y + i / 3 - 1, H), rx = reflect1(x + i % 3 - 1, W);
+    WarpPt p;
+    warp_point<F>(cam, A, rx, ry, __ldg(c.tdep + (ry * W + rx)), p);
+    const TapIdx ti = make_taps(p, H, W);
+    float t[3], w[3];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float w = blend(load_taps(c.ref, ch * c.ref_sc, ti, W), ti);
-            const float t = __ldg(c.tgt + (ch * c.tgt_sc + pix));
-            if (i == 0) { sx[ch] = 0.f; sy[ch] = 0.f; sxx[ch] = 0.f; syy[ch] = 0.f; sxy[ch] = 0.f; }
-            sx[ch] = __fadd_rn(sx[ch], t);
-            sy[ch] = __fadd_rn(sy[ch], w);
-            sxx[ch] = __fadd_rn(sxx[ch], __fmul_rn(t, t));
-            syy[ch] = __fadd_rn(syy[ch], __fmul_rn(w, w));
-            sxy[ch] = __fadd_rn(sxy[ch], __fmul_rn(t, w));
-            if (i == 4) { tc[ch] = t; wc[ch] = w; }
-        }
-        if (i == 4 && need_depth) dd = depth_inconsistency(p.Z, blend(load_taps(c.rdep, 0, ti, W), ti));
+    for (int ch = 0; ch < 3; ++ch) {
+        w[ch] = blend(load_taps(c.ref, ch * c.ref_sc, ti, W), ti);
+        t[ch] = __ldg(c.tgt + (ch * c.tgt_sc + ry * W + rx));
     }
+    float dd = need_depth ? depth_inconsistency(p.Z, blend(load_taps(c.rdep, 0, ti, W), ti)) : 0.f;
+    const int seg = threadIdx.x & 16;                      // first lane of this task inside the warp
+    dd = __shfl_sync(0xffffffffu, dd, seg + 4);
     float esum = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
+        float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;        // like ssim_stats: row-major from zero
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float tk = __shfl_sync(0xffffffffu, t[ch], seg + k), wk = __shfl_sync(0xffffffffu, w[ch], seg + k);
+            sx = __fadd_rn(sx, tk);
+            sy = __fadd_rn(sy, wk);
+            sxx = __fadd_rn(sxx, __fmul_rn(tk, tk));
+            syy = __fadd_rn(syy, __fmul_rn(wk, wk));
+            sxy = __fadd_rn(sxy, __fmul_rn(tk, wk));
+        }
+        const float tc = __shfl_sync(0xffffffffu, t[ch], seg + 4), wc = __shfl_sync(0xffffffffu, w[ch], seg + 4);
         SsimStats s;
-        s.mu_x = div9_exact(sx[ch]);
-        s.mu_y = div9_exact(sy[ch]);
-        s.sig_x = __fsub_rn(div9_exact(sxx[ch]), __fmul_rn(s.mu_x, s.mu_x));
-        s.sig_y = __fsub_rn(div9_exact(syy[ch]), __fmul_rn(s.mu_y, s.mu_y));
-        s.sig_xy = __fsub_rn(div9_exact(sxy[ch]), __fmul_rn(s.mu_x, s.mu_y));
+        s.mu_x = div9_exact(sx);
+        s.mu_y = div9_exact(sy);
+        s.sig_x = __fsub_rn(div9_exact(sxx), __fmul_rn(s.mu_x, s.mu_x));
+        s.sig_y = __fsub_rn(div9_exact(syy), __fmul_rn(s.mu_y, s.mu_y));
+        s.sig_xy = __fsub_rn(div9_exact(sxy), __fmul_rn(s.mu_x, s.mu_y));
         const SsimTerms tt = ssim_terms(s, L.C1, L.C2);
-        const float l1 = clamp01_nan(fabsf(__fsub_rn(tc[ch], wc[ch])));
-        const float e = __fadd_rn(__fmul_rn(l1, L.w_l1), __fmul_rn(clamp01_nan(tt.raw), L.w_ssim));
-        esum = (ch == 0) ? e : __fadd_rn(esum, e);
+        const float l1 = clamp01_nan(fabsf(__fsub_rn(tc, wc)));
+        const float ev = __fadd_rn(__fmul_rn(l1, L.w_l1), __fmul_rn(clamp01_nan(tt.raw), L.w_ssim));
+        esum = (ch == 0) ? ev : __fadd_rn(esum, ev);
     }
     const float diff0 = mean3_of_sum<F>(esum, A);
-    return need_depth ? __fmul_rn(diff0, __fsub_rn(1.0f, dd)) : diff0;
+    if (live && sub == 0) g.diff_img[pix] = need_depth ? __fmul_rn(diff0, __fsub_rn(1.0f, dd)) : diff0;
 }
 
-// one thread per (listed pixel, competing group): overwrite the group's diff_img entry with the exact value
-template <int F>
-__global__ void __launch_bounds__(128)
-tie_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, const int* __restrict__ tie_list,
-                   const int* __restrict__ tie_count, int capacity) {
-    const int count = min(__ldg(tie_count), capacity);
-    const int task = blockIdx.x * 128 + threadIdx.x;
-    const int e = task / n_groups, j = task - e * n_groups;
-    if (e >= count) return;
-    const int n = L.A.H * L.A.W;
-    const int pix = __ldg(tie_list + e);
-    const int b = pix / n, r = pix - b * n;
-    const int y = r / L.A.W, x = r - y * L.A.W;
-    const tcsfm_pair_group& g = L.g[j];
-    g.diff_img[pix] = exact_pair_diff<F>(g, L, b, x, y);
+// CTAs of a persistent launch: one wave, SM count x CTAs resident per SM (TCSFM_PERSIST_CTAS overrides it: the tests
+// force a few CTAs to walk many tasks each)
+static int persistent_ctas(int per_sm) {
+    static int sms = 0;
+    if (const char* e = getenv("TCSFM_PERSIST_CTAS")) { const int v = atoi(e); if (v > 0) return v; }
+#ifndef TCSFM_HOST_EMU
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+#else
+    sms = 148;
+#endif
+    return sms * per_sm;
 }
 
 static int fill_launch(PairLaunch& L, const tcsfm_pair_group* groups, int n, int B, int H, int W,
@@ -781,7 +821,9 @@ extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
         for (int i = 0; i < n; ++i)
             L.vec16 = L.vec16 && aligned16(L.g[i].coef) && aligned16(L.g[i].mask) && aligned16(L.g[i].g_diff) &&
                       aligned16(L.g[i].min_base) && L.g[i].min_stride % 4 == 0;
-        dim3 grid(tiles, B, n), block(kTileThreads);
+        L.B = B; L.n_groups = n;
+        const int64_t total = (int64_t)tiles * B * n;
+        dim3 grid((unsigned)(total < persistent_ctas(TCSFM_BWD_MIN_BLOCKS) ? total : persistent_ctas(TCSFM_BWD_MIN_BLOCKS))), block(kTileThreads);
         TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(pair_bwd_kernel<F>, grid, block, smem, stream, L));
         if (int rc = check_launch("tcsfm_pair_loss_bwd")) return rc;
     }
@@ -801,7 +843,7 @@ extern "C" int tcsfm_pair_tie_resolve(const tcsfm_pair_group* groups, int n_grou
     for (int i = 0; i < n_groups; ++i)
         if (!L.g[i].diff_img) { set_error("tcsfm_pair_tie_resolve: group %d has no diff_img", i); return 1; }
     const int64_t tasks = (int64_t)capacity * n_groups;
-    dim3 grid((unsigned)((tasks + 127) / 128)), block(128);
+    dim3 grid((unsigned)((tasks + kTieTasksPerBlock - 1) / kTieTasksPerBlock)), block(16 * kTieTasksPerBlock);
     TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(tie_resolve_kernel<F>, grid, block, 0, stream, L, n_groups, tie_list, tie_count, capacity));
     return check_launch("tcsfm_pair_tie_resolve");
 }
