@@ -69,7 +69,10 @@ TRAIN_WORKLOADS = {
 }
 METRIC = "warp+SSIM/L1 loss fwd+bwd frames/s at 192x640"
 ARITH_MODES = ("exact", "fast")
-DEFAULT_ARITH = "exact"
+# the benchmarked default: the "fast" SSIM arithmetic passes the north-star parity gates on the GPU (loss 1e-5, gradients
+# 1e-4, every mask bit-exact; tests/test_gpu_parity.py::test_fast_*); "exact" (bit-identical diff_img as well) is timed in
+# the same run and reported under "other_arithmetic"
+DEFAULT_ARITH = "fast"
 N_INPUT_SETS = 8      # rotating input sets: 8 x ~47 MB > 126 MB of L2, so no step finds its inputs in L2
 
 
@@ -690,22 +693,43 @@ def main():
     other = None
     alt = "exact" if args.arith == "fast" else "fast"
     if args.only is None and rank == 0 and args.workload == "kitti" and alt in ops.PAIR_ARITHMETICS:
-        # the same workload through the other SSIM arithmetic flavour (both are reported every run)
+        # the same workload through the other SSIM arithmetic flavour (both are reported every run): CUDA-graph replay of
+        # the full step like the headline, per-launch times of the pair kernels from an eager pass
         ops.set_arithmetic(alt)
-        for i in range(5):
-            step_eager(i)
-        t_alt = _timing.KernelTimer()
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with _timing.record(t_alt):
+        alt_ms = None
+        if graphs is not None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for s_ in sets:
+                    for _ in range(3):
+                        run_step(loss_mod, s_, n_src)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            alt_graphs = []
+            for s_ in sets:
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    run_step(loss_mod, s_, n_src)
+                alt_graphs.append(g_)
+            for i in range(min(args.warmup, 5)):
+                alt_graphs[i % N_INPUT_SETS].replay()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
+            for i in range(args.steps):
+                alt_graphs[i % N_INPUT_SETS].replay()
+            a1.record()
+            torch.cuda.synchronize()
+            alt_ms = a0.elapsed_time(a1) / args.steps
+        t_alt = _timing.KernelTimer()
+        with _timing.record(t_alt):
             for i in range(eager_steps):
                 step_eager(i)
-            a1.record()
         k_alt = t_alt.summary()
-        other = {"arithmetic": alt, "launch": "eager", "ms_per_step": a0.elapsed_time(a1) / eager_steps,
-                 "value": wl["b"] / (a0.elapsed_time(a1) / eager_steps / 1e3), "unit": "frames/s",
-                 "kernels": {k: v for k, v in k_alt.items() if k.startswith("pair_loss")}}
+        other = {"arithmetic": alt, "launch": config["launch"], "ms_per_step": alt_ms,
+                 "value": (wl["b"] / (alt_ms / 1e3)) if alt_ms else None, "unit": "frames/s",
+                 "kernels": {k: v for k, v in k_alt.items() if k.startswith("pair_")}}
         ops.set_arithmetic(args.arith)
     eager_cuda = None
     if args.only is None and rank == 0:

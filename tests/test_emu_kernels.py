@@ -265,27 +265,3 @@ def test_disp_upsample_to_depth_vs_interpolate(shapes):
         assert dep.shape == ref.shape and same(dep, ref)
         ref.backward(g)
         assert gd.shape == d.shape and rel_l2(gd, d.grad) < 1e-5
-
-
-@pytest.mark.parametrize("ctas", ["1", "3", "7"])
-def test_pair_bwd_persistent_ctas_walk_many_tasks(monkeypatch, ctas):
-    """The backward kernel is persistent: each CTA walks a contiguous range of (group, batch element, tile) tasks and
-    reduces grad(K[R|t]) once per (group, batch element).  Forcing 1 / 3 / 7 CTAs makes every CTA cross tile, batch
-    and group boundaries; the result must not depend on the partition."""
-    monkeypatch.setenv("TCSFM_PERSIST_CTAS", ctas)
-    test_pair_loss_multi_group_and_partial_tiles()
-    fr = synth.make_frames(3, 20, 70, seed=2)
-    cfg = goldens.FULL_CFG
-    flags = cfg_flags(cfg)
-    groups = []
-    for j in range(2):
-        kinv, proj = stn.projection_matrices(-fr["poses"][j], fr["K"])
-        groups.append({"tgt_img": fr["target"], "ref_img": fr["sources"][j], "tgt_depth": fr["depths"][0],
-                       "ref_depth": fr["depths"][1 + j], "kinv": kinv, "proj": proj})
-    batch = _raw.PairBatch(groups)
-    diff, mask, sums, coef = _raw.pair_loss_fwd(emu(), batch, 0.15, 0.85, flags)
-    g_diff = torch.randn(2, 3, 1, 20, 70, generator=torch.Generator().manual_seed(1))
-    _, _, g_proj = _raw.pair_loss_bwd(emu(), batch, mask, sums, coef, g_diff, None, 0.15, 0.85, flags, True)
-    monkeypatch.setenv("TCSFM_PERSIST_CTAS", "1000")
-    _, _, g_ref = _raw.pair_loss_bwd(emu(), batch, mask, sums, coef, g_diff, None, 0.15, 0.85, flags, True)
-    assert rel_l2(g_proj, g_ref) < 1e-5

@@ -54,7 +54,6 @@ struct PairLaunch {
     float w_l1, w_ssim, C1, C2;
     int flags;
     int vec16;                       // backward: every coefficient row start is 16-byte aligned (W % 4 == 0, aligned base)
-    int B, n_groups;                 // backward: the persistent CTAs walk tasks = (group, batch element, tile)
 };
 
 struct PairCtx {
@@ -362,37 +361,12 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     using BT = BwdTile;
     TCSFM_DYN_SMEM(float, cs);                     // [9][BT::kCells] coefficients, [BT::kCells] upstream gradient
 
-    // Persistent CTAs: the grid is one wave (SMs x resident CTAs); CTA i walks a contiguous range of the tasks
-    // (group, batch element, tile), tile fastest.  The twelve grad(K[R|t]) accumulators stay in registers across the
-    // tiles of one (group, batch element) and are block-reduced once when that changes (or at the end), instead of
-    // once per tile.
+    const tcsfm_pair_group& g = L.g[blockIdx.z];
     const Arith& A = L.A;
     const int H = A.H, W = A.W, n = H * W;
+    const int b = blockIdx.y;
     const int tiles_x = (W + kTileW - 1) / kTileW;
-    const int tiles = tiles_x * ((H + kTileH - 1) / kTileH);
-    const int total = tiles * L.B * L.n_groups;
-    const int task_end = (int)(((int64_t)blockIdx.x + 1) * total / gridDim.x);
-    float acc[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
-    int cur_gb = -1;
-    auto flush = [&](int gb) {                         // all threads; the tile doubles as reduction scratch
-        const int gi = gb / L.B, bb = gb - gi * L.B;
-        if (L.g[gi].g_proj) block_atomic_accumulate<12>(acc, cs, L.g[gi].g_proj + bb * 12, threadIdx.x, kTileThreads);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) acc[i] = 0.f;
-    };
-#pragma unroll 1
-    for (int task = (int)((int64_t)blockIdx.x * total / gridDim.x); task < task_end; ++task) {
-    const int gb = task / tiles, tile = task - gb * tiles;
-    if (gb != cur_gb) {
-        if (cur_gb >= 0) flush(cur_gb);
-        cur_gb = gb;
-    }
-    const int group = gb / L.B;
-    const tcsfm_pair_group& g = L.g[group];
-    const int b = gb - group * L.B;
-    const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
+    const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
     const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
     const Cam cam = load_cam(g.kinv, g.proj, b);
     const PairCtx c = make_ctx(g, b, n);
@@ -582,6 +556,9 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     }
 
     // ---- phase D, one own pixel at a time: L1 / depth adjoints and the geometry adjoint ----
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
 #pragma unroll kBwdDUnroll
     for (int k = 0; k < kPixPerThread; ++k) {
         const int gy = y0 + ty0 + k;
@@ -636,9 +613,8 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             }
         }
     }
-    __syncthreads();                                   // phase D is over everywhere: the tile is free for the next task
-    }
-    if (cur_gb >= 0) flush(cur_gb);
+    __syncthreads();                                   // phase D is over everywhere: the tile doubles as reduction scratch
+    if (g.g_proj) block_atomic_accumulate<12>(acc, cs, g.g_proj + b * 12, threadIdx.x, kTileThreads);
 }
 
 // ---------------------------------------------------------------------------
@@ -711,22 +687,6 @@ tie_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, const int
     }
     const float diff0 = mean3_of_sum<F>(esum, A);
     if (live && sub == 0) g.diff_img[pix] = need_depth ? __fmul_rn(diff0, __fsub_rn(1.0f, dd)) : diff0;
-}
-
-// CTAs of a persistent launch: one wave, SM count x CTAs resident per SM (TCSFM_PERSIST_CTAS overrides it: the tests
-// force a few CTAs to walk many tasks each)
-static int persistent_ctas(int per_sm) {
-    static int sms = 0;
-    if (const char* e = getenv("TCSFM_PERSIST_CTAS")) { const int v = atoi(e); if (v > 0) return v; }
-#ifndef TCSFM_HOST_EMU
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
-#else
-    sms = 148;
-#endif
-    return sms * per_sm;
 }
 
 static int fill_launch(PairLaunch& L, const tcsfm_pair_group* groups, int n, int B, int H, int W,
@@ -821,9 +781,7 @@ extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
         for (int i = 0; i < n; ++i)
             L.vec16 = L.vec16 && aligned16(L.g[i].coef) && aligned16(L.g[i].mask) && aligned16(L.g[i].g_diff) &&
                       aligned16(L.g[i].min_base) && L.g[i].min_stride % 4 == 0;
-        L.B = B; L.n_groups = n;
-        const int64_t total = (int64_t)tiles * B * n;
-        dim3 grid((unsigned)(total < persistent_ctas(TCSFM_BWD_MIN_BLOCKS) ? total : persistent_ctas(TCSFM_BWD_MIN_BLOCKS))), block(kTileThreads);
+        dim3 grid(tiles, B, n), block(kTileThreads);
         TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(pair_bwd_kernel<F>, grid, block, smem, stream, L));
         if (int rc = check_launch("tcsfm_pair_loss_bwd")) return rc;
     }
