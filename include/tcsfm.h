@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 10
+#define TCSFM_ABI_VERSION 11
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -206,6 +206,11 @@ int tcsfm_smooth_fwd(const float* disp, const float* img, int64_t img_sb, int64_
                      float* workspace, float* out, int B, int H, int W, void* stream);
 int tcsfm_smooth_bwd(const float* disp, const float* img, int64_t img_sb, int64_t img_sc,
                      float* workspace, const float* g_out, float* g_disp, int B, int H, int W, void* stream);
+
+/* ---- data format at the host boundary: the reference's loader turns uint8 frames into float tensors on the host
+ *      (utils/custom_transforms.py:74: torch.from_numpy(im).float() / 255) and ships fp32 to the GPU.  dst[i] =
+ *      float(src[i]) / 255 with the same IEEE division, so frames can cross the host link as bytes. */
+int tcsfm_u8_to_float(const unsigned char* src, float* dst, int64_t n, void* stream);
 
 /* ---- glue of Compute_Loss.forward (losses.py:75-140) ----------------------------
  * pose [N,6] (times `sign`; every call site passes -pose) -> K @ [Rx Ry Rz | t] as [N,12]

@@ -531,3 +531,16 @@ def test_ssim_mean_matches_map_mean(emu_ops):
     (3.0 * a).sum().backward()
     (3.0 * b).backward()
     assert rel_l2(xa.grad, xb.grad) < 1e-5
+
+
+def test_images_from_uint8_matches_the_loader_conversion(emu_ops):
+    """utils/custom_transforms.py:74: torch.from_numpy(im).float() / 255 -- every byte value, odd lengths, views."""
+    from tcsfm_b200 import dataformat
+    u8 = torch.arange(0, 256, dtype=torch.uint8).repeat(5)[:1277].reshape(1, 1, 1, 1277)
+    assert torch.equal(dataformat.images_from_uint8(u8), u8.float() / 255)
+    img = torch.randint(0, 256, (2, 3, 13, 21), dtype=torch.uint8, generator=torch.Generator().manual_seed(0))
+    out = torch.empty(2, 3, 13, 21)
+    assert dataformat.images_from_uint8(img, out) is out and torch.equal(out, img.float() / 255)
+    assert torch.equal(dataformat.images_from_uint8(img[:, :, 1:, 3:]), img[:, :, 1:, 3:].float() / 255)
+    with pytest.raises(TypeError):
+        dataformat.images_from_uint8(out)

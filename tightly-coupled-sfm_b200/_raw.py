@@ -168,6 +168,23 @@ def ssim_mean_bwd(lib, x, y, g_mean, need_x=True, need_y=True, flags=0):
     return g_x, g_y
 
 
+def u8_to_float(lib, src, out=None):
+    """float(src) / 255 (the loader's conversion, utils/custom_transforms.py:74) of a uint8 tensor; `out`: optional
+    preallocated fp32 tensor of the same shape (e.g. the static input buffer of a CUDA graph)."""
+    if src.dtype != torch.uint8:
+        raise TypeError("u8_to_float expects a uint8 tensor, got %s" % src.dtype)
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    elif out.dtype != torch.float32 or out.shape != src.shape or not out.is_contiguous():
+        raise ValueError("u8_to_float: `out` must be a contiguous fp32 tensor of the input's shape")
+    with _timing.launch("u8_to_float", src.is_cuda):
+        rc = lib.tcsfm_u8_to_float(_ptr(src), _ptr(out), src.numel(), _stream(src))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return out
+
+
 class PairBatch:
     """Host-side descriptor array for one multi-group pair-loss launch; keeps every
     tensor it points at alive."""

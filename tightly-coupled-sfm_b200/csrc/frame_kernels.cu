@@ -201,6 +201,25 @@ disp_up_to_depth_bwd_kernel(const __grid_constant__ MapPtrs M, UpShape U, float 
     }
 }
 
+// uint8 image -> float in [0, 1] exactly like the reference's loader does on the host
+// (utils/custom_transforms.py:74: torch.from_numpy(im).float() / 255, a true IEEE division), four pixels per thread:
+// the images can then cross the host link as bytes (a quarter of the fp32 traffic).
+__global__ void __launch_bounds__(256)
+u8_to_float_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i + 3 < n && (reinterpret_cast<uintptr_t>(src + i) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst + i) & 15) == 0) {
+        const unsigned v = *reinterpret_cast<const unsigned*>(src + i);
+        float4 o;
+        o.x = __fdiv_rn((float)(v & 255u), 255.0f);
+        o.y = __fdiv_rn((float)((v >> 8) & 255u), 255.0f);
+        o.z = __fdiv_rn((float)((v >> 16) & 255u), 255.0f);
+        o.w = __fdiv_rn((float)(v >> 24), 255.0f);
+        *reinterpret_cast<float4*>(dst + i) = o;
+    } else {
+        for (int64_t k = i; k < n && k < i + 4; ++k) dst[k] = __fdiv_rn((float)src[k], 255.0f);
+    }
+}
+
 constexpr int kReduceThreads = 256;
 
 __global__ void __launch_bounds__(kReduceThreads)
@@ -294,6 +313,14 @@ __global__ void frame_bwd_prepare_kernel(const float* __restrict__ g_out, const 
 }  // namespace tcsfm
 
 using namespace tcsfm;
+
+extern "C" int tcsfm_u8_to_float(const unsigned char* src, float* dst, int64_t n, void* stream) {
+    if (!src || !dst || n <= 0) { set_error("tcsfm_u8_to_float: bad arguments"); return 1; }
+    const int64_t blocks = (n + 1023) / 1024;
+    if (blocks >= ((int64_t)1 << 31)) { set_error("tcsfm_u8_to_float: too many elements"); return 1; }
+    TCSFM_LAUNCH(u8_to_float_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, src, dst, n);
+    return check_launch("tcsfm_u8_to_float");
+}
 
 extern "C" int tcsfm_min_reduce_ties(const float* base, int64_t stride, int count, int64_t n, float* out_sum, float band,
                                      int* tie_list, int* tie_count, int capacity, void* stream) {
