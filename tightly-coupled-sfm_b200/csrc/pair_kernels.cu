@@ -30,6 +30,9 @@
 //      adjoint: grad(target depth) is a direct store, grad(source depth) a 4-tap atomic
 //      scatter, grad(K[R|t]) 12 block-reduced accumulators per batch element.
 #include "tile.cuh"
+#ifndef TCSFM_HOST_EMU
+#include <cuda.h>                  // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint: no libcuda link)
+#endif
 
 namespace tcsfm {
 
@@ -54,6 +57,9 @@ struct PairLaunch {
     float w_l1, w_ssim, C1, C2;
     int flags;
     int vec16;                       // backward: every coefficient row start is 16-byte aligned (W % 4 == 0, aligned base)
+#ifndef TCSFM_HOST_EMU
+    alignas(64) CUtensorMap coef_map[kMaxGroups];   // backward, TMA staging: the group's workspace as a [B][10][H][W] tensor
+#endif
 };
 
 struct PairCtx {
@@ -355,11 +361,58 @@ struct BwdTile {
 constexpr size_t kBwdSmemBytes = 10 * BwdTile::kCells * sizeof(float);
 static_assert(4 * (kBwdSmemBytes + 1024) <= 196 * 1024, "four backward CTAs must fit the 196 KB shared-memory carve-out");
 
-template <int F>
+// TMA staging (kTma): one cp.async.bulk.tensor brings the nine coefficient planes of the tile + 1 ring -- a
+// 68 x 18 x 9 box of the group's [B][10][H][W] workspace starting at (x0 - 3, y0 - 1, plane 0) -- into shared memory;
+// rows / columns outside the image arrive as zeros (the tensor map's out-of-bounds fill), so the staging needs no
+// per-thread address arithmetic, predicates or cp.async instructions at all.  The box is dense: plane stride 68 * 18,
+// cell (cx, cy) at (cy + 1) * 68 + cx + 3.  The upstream-gradient plane keeps the layout above (threads write it).
+struct TmaTile {
+    static constexpr int kBoxW = kTileW + 4, kBoxH = kTileH + 2, kPlanes = 9;
+    static constexpr int kPlane = kBoxW * kBoxH;                                   // floats per plane
+    static constexpr unsigned kBytes = kPlane * kPlanes * sizeof(float);
+    __device__ __forceinline__ static int cell(int cx, int cy) { return (cy + 1) * kBoxW + cx + 3; }
+};
+constexpr size_t kBwdTmaSmemBytes = (TmaTile::kPlane * 9 + BwdTile::kCells) * sizeof(float) + 16;      // + the mbarrier
+static_assert(4 * (kBwdTmaSmemBytes + 1024) <= 196 * 1024, "four backward CTAs must fit the 196 KB shared-memory carve-out");
+static_assert((TmaTile::kPlane * 9 + BwdTile::kCells) * sizeof(float) % 8 == 0, "mbarrier alignment");
+
+#ifndef TCSFM_HOST_EMU
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarrier_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbarrier_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, void* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 :: "r"(smem_addr(dst)), "l"(map), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// waits for phase `parity`; a transfer that never completes (bad descriptor) traps instead of hanging the GPU
+__device__ __forceinline__ void mbarrier_wait(void* bar, unsigned parity) {
+    for (unsigned spin = 0;; ++spin) {
+        unsigned done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (done) return;
+        if (spin > (1u << 24)) __trap();
+    }
+}
+#endif
+
+template <int F, bool kTma>
 __global__ void __launch_bounds__(kTileThreads, TCSFM_BWD_MIN_BLOCKS)
 pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     using BT = BwdTile;
-    TCSFM_DYN_SMEM(float, cs);                     // [9][BT::kCells] coefficients, [BT::kCells] upstream gradient
+#ifndef TCSFM_HOST_EMU
+    extern __shared__ __align__(128) unsigned char cs_raw_[];
+    float* cs = reinterpret_cast<float*>(cs_raw_);  // [9][plane] coefficients, [BT::kCells] upstream gradient (, mbarrier)
+#else
+    TCSFM_DYN_SMEM(float, cs);
+#endif
+    constexpr int kPlane = kTma ? TmaTile::kPlane : BT::kCells;       // floats per coefficient plane in shared memory
+    auto pcell = [](int cx, int cy) { return kTma ? TmaTile::cell(cx, cy) : BT::cell(cx, cy); };
 
     const tcsfm_pair_group& g = L.g[blockIdx.z];
     const Arith& A = L.A;
@@ -385,7 +438,18 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     // ---- phase B: the nine coefficient planes of the tile + 1 ring go global -> shared with
     //      cp.async (no register staging, all loads in flight at once; zero fill outside the
     //      image), next to the upstream gradient of diff_img at each ring pixel ----
-    float* Gs = cs + 9 * BT::kCells;               // [cells] upstream gradient (0 outside the image)
+    float* Gs = cs + 9 * kPlane;                   // [BT::kCells] upstream gradient (0 outside the image)
+#ifndef TCSFM_HOST_EMU
+    void* bar = Gs + BT::kCells;
+    if (kTma) {
+        if (threadIdx.x == 0) mbarrier_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbarrier_expect_tx(bar, TmaTile::kBytes);
+            tma_load_4d(cs, &L.coef_map[blockIdx.z], bar, x0 - 3, y0 - 1, 0, b);
+        }
+    }
+#endif
     const bool two_way = sc.min_other != nullptr;                    // per-pixel min over exactly two sources
     // Upstream gradient of one pixel from its loaded ingredients (mask, explicit grad, own / other
     // min-reprojection candidate); torch.min(dim): the first index holding the minimum wins, a NaN is the minimum.
@@ -426,8 +490,10 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
                 const int at = row * BT::kPitch + 4 + 4 * chunk;
                 *reinterpret_cast<float4*>(Gs + at) = G4;
                 const bool live = (G4.x != 0.f) || (G4.y != 0.f) || (G4.z != 0.f) || (G4.w != 0.f);
+                if (!kTma) {
 #pragma unroll
-                for (int j = 0; j < 9; ++j) async_copy16(cs + j * BT::kCells + at, coef + (j * n + pix), live);
+                    for (int j = 0; j < 9; ++j) async_copy16(cs + j * BT::kCells + at, coef + (j * n + pix), live);
+                }
             } else {
                 const int h2 = task - kChunkTasks;
                 const int row = h2 >> 1, cx = (h2 & 1) ? kTileW : -1;
@@ -440,8 +506,10 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
                 const int at = BT::cell(cx, row - 1);
                 Gs[at] = Gd;
                 const bool live = Gd != 0.f;
+                if (!kTma) {
 #pragma unroll
-                for (int j = 0; j < 9; ++j) async_copy4(cs + j * BT::kCells + at, coef + (j * n + pix), live);
+                    for (int j = 0; j < 9; ++j) async_copy4(cs + j * BT::kCells + at, coef + (j * n + pix), live);
+                }
             }
         };
         stage_task(threadIdx.x);
@@ -484,6 +552,9 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     }
     __pipeline_commit();
     __pipeline_wait_prior(0);
+#ifndef TCSFM_HOST_EMU
+    if (kTma) mbarrier_wait(bar, 0);
+#endif
     __syncthreads();
 
     // ---- phase C: separable 3x3 sums of the nine coefficient planes down the strip with a
@@ -505,19 +576,24 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         // even columns pair (c, c+1) and take c-1 alone, odd columns pair (c-1, c) and take c+1 alone
         // (two shared-memory wavefronts per warp instead of three).  The upstream weights are permuted
         // to match; a border neighbour that reflection folds back counts twice.
-        const int par = tx & 1;
+        // (The TMA box starts three columns left of the tile, so its centre cells have the opposite parity of the
+        // upstream plane's: the weights are formed in (left, centre, right) order and permuted per layout.)
+        const int par = tx & 1;                              // parity of the centre cell in the upstream plane
+        const int ppar = kTma ? (par ^ 1) : par;             // ... and in the coefficient planes
         const float dup_l = (gx == 1) ? 2.f : 1.f, dup_r = (gx == W - 2) ? 2.f : 1.f;
-        const float f_a = par ? dup_l : 1.f, f_b = par ? 1.f : dup_r, f_c = par ? dup_r : dup_l;
-        const int single_at = par ? 2 : -1;                  // offset of the single cell from the pair
+        const int g_single = par ? 2 : -1, p_single = ppar ? 2 : -1;      // offset of the single cell from the pair
         auto hsum = [&](int r, float (&out)[9]) {          // horizontal 3-sums of tile row ty0 - 1 + r
-            const int c0 = BT::cell(tx, ty0 - 1 + r) - par;  // even: the pair starts at the centre cell
-            const float2 gp = *reinterpret_cast<const float2*>(Gs + c0);
-            const float wa = gp.x * f_a, wb = gp.y * f_b, wc = Gs[c0 + single_at] * f_c;
+            const int g0 = BT::cell(tx, ty0 - 1 + r) - par;  // even: the pair starts at the centre cell
+            const float2 gp = *reinterpret_cast<const float2*>(Gs + g0);
+            const float gs = Gs[g0 + g_single];
+            const float wl = (par ? gp.x : gs) * dup_l, wm = par ? gp.y : gp.x, wr = (par ? gs : gp.y) * dup_r;
+            const float wa = ppar ? wl : wm, wb = ppar ? wm : wr, wc = ppar ? wr : wl;     // (pair.x, pair.y, single)
+            const int c0 = pcell(tx, ty0 - 1 + r) - ppar;
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
-                const float* pl = cs + j * BT::kCells + c0;
+                const float* pl = cs + j * kPlane + c0;
                 const float2 pr = *reinterpret_cast<const float2*>(pl);
-                out[j] = pr.x * wa + pr.y * wb + pl[single_at] * wc;
+                out[j] = pr.x * wa + pr.y * wb + pl[p_single] * wc;
             }
         };
         hsum(0, h[1]);
@@ -550,9 +626,9 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
 #pragma unroll
         for (int k = 0; k < kPixPerThread; ++k)
 #pragma unroll
-            for (int j = 0; j < 6; ++j) cs[j * BT::kCells + BT::cell(tx, ty0 + k)] = pq[k][j];
+            for (int j = 0; j < 6; ++j) cs[j * kPlane + pcell(tx, ty0 + k)] = pq[k][j];
 #pragma unroll
-        for (int k = 0; k < kPixPerThread; ++k) cs[6 * BT::kCells + BT::cell(tx, ty0 + k)] = dep_own[k];
+        for (int k = 0; k < kPixPerThread; ++k) cs[6 * kPlane + pcell(tx, ty0 + k)] = dep_own[k];
     }
 
     // ---- phase D, one own pixel at a time: L1 / depth adjoints and the geometry adjoint ----
@@ -564,13 +640,13 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         const int gy = y0 + ty0 + k;
         if (gx < W && gy < H) {
             const int pix = gy * W + gx;
-            const int cell = BT::cell(tx, ty0 + k);
-            const float dep = cs[6 * BT::kCells + cell], m = __ldg(mask + pix);
+            const int cell = pcell(tx, ty0 + k);
+            const float dep = cs[6 * kPlane + cell], m = __ldg(mask + pix);
             const float d0 = depth_mask ? __ldg(coef + (9 * n + pix)) : 0.f;
             WarpPt p;
             warp_point<F>(cam, A, gx, gy, dep, p);
             const TapIdx ti = make_taps(p, H, W);
-            const float Gd = Gs[cell];
+            const float Gd = Gs[BT::cell(tx, ty0 + k)];
             // d loss / d dd = c_dep * mask - Gd * diff0   (diff = diff0 * (1 - dd), losses.py:176-177)
             const float Gdd = sc.c_dep * m - Gd * d0;
             float pd = 0.f, dd = 0.f;
@@ -589,7 +665,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
                 const float w = blend(tv, ti);
                 const float t = __ldg(c.tgt + (ch * c.tgt_sc + pix));
                 const float dlt = t - w;
-                float gwc = cs[(2 * ch) * BT::kCells + cell] + w * cs[(2 * ch + 1) * BT::kCells + cell];
+                float gwc = cs[(2 * ch) * kPlane + cell] + w * cs[(2 * ch + 1) * kPlane + cell];
                 if (fabsf(dlt) <= 1.0f) gwc += (dlt > 0.f) ? -gl1 : ((dlt < 0.f) ? gl1 : 0.f);
                 bilinear_grad(tv, p, gwc, g_ix, g_iy);
             }
@@ -689,6 +765,39 @@ tie_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, const int
     if (live && sub == 0) g.diff_img[pix] = need_depth ? __fmul_rn(diff0, __fsub_rn(1.0f, dd)) : diff0;
 }
 
+#ifndef TCSFM_HOST_EMU
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        if (getenv("TCSFM_NO_TMA")) return nullptr;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// The workspace of one group as a rank-4 fp32 tensor [B][10][H][W] with a 68 x 18 x 9 x 1 box; out-of-bounds elements
+// (the halo outside the image) are filled with zeros.
+static bool encode_coef_map(CUtensorMap* map, const float* coef, int B, int H, int W) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || W % 4 != 0 || reinterpret_cast<uintptr_t>(coef) % 16 != 0) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)kCoefPlanes, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)kCoefPlanes * H * W * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)TmaTile::kBoxW, (cuuint32_t)TmaTile::kBoxH, (cuuint32_t)TmaTile::kPlanes, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(coef), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#endif
+
 static int fill_launch(PairLaunch& L, const tcsfm_pair_group* groups, int n, int B, int H, int W,
                        float w_l1, float w_ssim, int flags, const char* who, bool bwd) {
     if (B <= 0 || H < 2 || W < 2) { set_error("%s: bad shape B=%d H=%d W=%d", who, B, H, W); return 1; }
@@ -782,7 +891,20 @@ extern "C" int tcsfm_pair_loss_bwd(const tcsfm_pair_group* groups, int n_groups,
             L.vec16 = L.vec16 && aligned16(L.g[i].coef) && aligned16(L.g[i].mask) && aligned16(L.g[i].g_diff) &&
                       aligned16(L.g[i].min_base) && L.g[i].min_stride % 4 == 0;
         dim3 grid(tiles, B, n), block(kTileThreads);
-        TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(pair_bwd_kernel<F>, grid, block, smem, stream, L));
+        bool tma = false;
+#ifndef TCSFM_HOST_EMU
+        // TMA staging of the coefficient planes when every group's workspace can be described by a tensor map
+        // (16-byte aligned rows); otherwise the cp.async staging
+        tma = L.vec16 != 0;
+        for (int i = 0; i < n && tma; ++i) tma = encode_coef_map(&L.coef_map[i], L.g[i].coef, B, H, W);
+        if (tma) {
+            cudaError_t e = cudaSuccess;
+            TCSFM_DISPATCH_FLAVOUR(flags, e = cudaFuncSetAttribute(pair_bwd_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTmaSmemBytes));
+            if (e != cudaSuccess) { set_error("tcsfm_pair_loss_bwd: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return 2; }
+            TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH((pair_bwd_kernel<F, true>), grid, block, kBwdTmaSmemBytes, stream, L));
+        }
+#endif
+        if (!tma) { TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH((pair_bwd_kernel<F, false>), grid, block, smem, stream, L)); }
         if (int rc = check_launch("tcsfm_pair_loss_bwd")) return rc;
     }
     return 0;
