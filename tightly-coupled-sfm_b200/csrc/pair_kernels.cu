@@ -361,17 +361,20 @@ struct BwdTile {
 constexpr size_t kBwdSmemBytes = 10 * BwdTile::kCells * sizeof(float);
 static_assert(4 * (kBwdSmemBytes + 1024) <= 196 * 1024, "four backward CTAs must fit the 196 KB shared-memory carve-out");
 
-// TMA staging (kTma): one cp.async.bulk.tensor brings the nine coefficient planes of the tile + 1 ring -- a
-// 68 x 18 x 9 box of the group's [B][10][H][W] workspace starting at (x0 - 3, y0 - 1, plane 0) -- into shared memory;
-// rows / columns outside the image arrive as zeros (the tensor map's out-of-bounds fill), so the staging needs no
-// per-thread address arithmetic, predicates or cp.async instructions at all.  The box is dense: plane stride 68 * 18,
-// cell (cx, cy) at (cy + 1) * 68 + cx + 3.  The upstream-gradient plane keeps the layout above (threads write it).
+// TMA staging (kTma): one cp.async.bulk.tensor brings the nine coefficient planes of the tile + its left halo and the
+// rows above / below -- a 68 x 18 x 9 box of the group's [B][10][H][W] workspace starting at (x0 - 4, y0 - 1, plane 0);
+// the innermost start coordinate must be a multiple of 16 bytes (measured: x0 - 3 raises an illegal-instruction fault)
+// -- into shared memory; rows / columns outside the image arrive as zeros (the tensor map's out-of-bounds fill), so
+// the staging needs no per-thread address arithmetic, predicates or cp.async instructions.  The dense box has exactly
+// the layout above (pitch 68, interior at column 4, left halo at column 3) with plane stride 68 * 18; the right halo
+// column (one value per row and plane) is loaded by 162 threads into registers before the wait and stored, like
+// above, into column 0 of the next row (which the box filled with an unused value).
 struct TmaTile {
     static constexpr int kBoxW = kTileW + 4, kBoxH = kTileH + 2, kPlanes = 9;
     static constexpr int kPlane = kBoxW * kBoxH;                                   // floats per plane
     static constexpr unsigned kBytes = kPlane * kPlanes * sizeof(float);
-    __device__ __forceinline__ static int cell(int cx, int cy) { return (cy + 1) * kBoxW + cx + 3; }
 };
+static_assert(TmaTile::kBoxW == BwdTile::kPitch && TmaTile::kBoxH == BwdTile::kRows, "the TMA box is the backward tile");
 constexpr size_t kBwdTmaSmemBytes = (TmaTile::kPlane * 9 + BwdTile::kCells) * sizeof(float) + 16;      // + the mbarrier
 static_assert(4 * (kBwdTmaSmemBytes + 1024) <= 196 * 1024, "four backward CTAs must fit the 196 KB shared-memory carve-out");
 static_assert((TmaTile::kPlane * 9 + BwdTile::kCells) * sizeof(float) % 8 == 0, "mbarrier alignment");
@@ -412,7 +415,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     TCSFM_DYN_SMEM(float, cs);
 #endif
     constexpr int kPlane = kTma ? TmaTile::kPlane : BT::kCells;       // floats per coefficient plane in shared memory
-    auto pcell = [](int cx, int cy) { return kTma ? TmaTile::cell(cx, cy) : BT::cell(cx, cy); };
+    auto pcell = [](int cx, int cy) { return BT::cell(cx, cy); };
 
     const tcsfm_pair_group& g = L.g[blockIdx.z];
     const Arith& A = L.A;
@@ -446,10 +449,19 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         __syncthreads();
         if (threadIdx.x == 0) {
             mbarrier_expect_tx(bar, TmaTile::kBytes);
-            tma_load_4d(cs, &L.coef_map[blockIdx.z], bar, x0 - 3, y0 - 1, 0, b);
+            tma_load_4d(cs, &L.coef_map[blockIdx.z], bar, x0 - 4, y0 - 1, 0, b);
         }
     }
 #endif
+    // the right halo column of the TMA path: plane j, tile row r (one value per thread, zero outside the image)
+    float rh_val = 0.f;
+    int rh_at = -1;
+    if (kTma && threadIdx.x < TmaTile::kPlanes * BT::kRows) {
+        const int j = threadIdx.x / BT::kRows, r = threadIdx.x - j * BT::kRows;
+        const int qy = y0 + r - 1, qx = x0 + kTileW;
+        rh_at = j * kPlane + BT::cell(kTileW, r - 1);
+        if (qy >= 0 && qy < H && qx < W) rh_val = __ldg(coef + (j * n + qy * W + qx));
+    }
     const bool two_way = sc.min_other != nullptr;                    // per-pixel min over exactly two sources
     // Upstream gradient of one pixel from its loaded ingredients (mask, explicit grad, own / other
     // min-reprojection candidate); torch.min(dim): the first index holding the minimum wins, a NaN is the minimum.
@@ -553,7 +565,10 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
     __pipeline_commit();
     __pipeline_wait_prior(0);
 #ifndef TCSFM_HOST_EMU
-    if (kTma) mbarrier_wait(bar, 0);
+    if (kTma) {
+        mbarrier_wait(bar, 0);
+        if (rh_at >= 0) cs[rh_at] = rh_val;             // after the box has landed: it wrote an unused value there
+    }
 #endif
     __syncthreads();
 
@@ -576,24 +591,19 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
         // even columns pair (c, c+1) and take c-1 alone, odd columns pair (c-1, c) and take c+1 alone
         // (two shared-memory wavefronts per warp instead of three).  The upstream weights are permuted
         // to match; a border neighbour that reflection folds back counts twice.
-        // (The TMA box starts three columns left of the tile, so its centre cells have the opposite parity of the
-        // upstream plane's: the weights are formed in (left, centre, right) order and permuted per layout.)
-        const int par = tx & 1;                              // parity of the centre cell in the upstream plane
-        const int ppar = kTma ? (par ^ 1) : par;             // ... and in the coefficient planes
+        const int par = tx & 1;
         const float dup_l = (gx == 1) ? 2.f : 1.f, dup_r = (gx == W - 2) ? 2.f : 1.f;
-        const int g_single = par ? 2 : -1, p_single = ppar ? 2 : -1;      // offset of the single cell from the pair
+        const float f_a = par ? dup_l : 1.f, f_b = par ? 1.f : dup_r, f_c = par ? dup_r : dup_l;
+        const int single_at = par ? 2 : -1;                  // offset of the single cell from the pair
         auto hsum = [&](int r, float (&out)[9]) {          // horizontal 3-sums of tile row ty0 - 1 + r
-            const int g0 = BT::cell(tx, ty0 - 1 + r) - par;  // even: the pair starts at the centre cell
-            const float2 gp = *reinterpret_cast<const float2*>(Gs + g0);
-            const float gs = Gs[g0 + g_single];
-            const float wl = (par ? gp.x : gs) * dup_l, wm = par ? gp.y : gp.x, wr = (par ? gs : gp.y) * dup_r;
-            const float wa = ppar ? wl : wm, wb = ppar ? wm : wr, wc = ppar ? wr : wl;     // (pair.x, pair.y, single)
-            const int c0 = pcell(tx, ty0 - 1 + r) - ppar;
+            const int c0 = BT::cell(tx, ty0 - 1 + r) - par;  // even: the pair starts at the centre cell
+            const float2 gp = *reinterpret_cast<const float2*>(Gs + c0);
+            const float wa = gp.x * f_a, wb = gp.y * f_b, wc = Gs[c0 + single_at] * f_c;
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
                 const float* pl = cs + j * kPlane + c0;
                 const float2 pr = *reinterpret_cast<const float2*>(pl);
-                out[j] = pr.x * wa + pr.y * wb + pl[p_single] * wc;
+                out[j] = pr.x * wa + pr.y * wb + pl[single_at] * wc;
             }
         };
         hsum(0, h[1]);
@@ -646,7 +656,7 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
             WarpPt p;
             warp_point<F>(cam, A, gx, gy, dep, p);
             const TapIdx ti = make_taps(p, H, W);
-            const float Gd = Gs[BT::cell(tx, ty0 + k)];
+            const float Gd = Gs[cell];
             // d loss / d dd = c_dep * mask - Gd * diff0   (diff = diff0 * (1 - dd), losses.py:176-177)
             const float Gdd = sc.c_dep * m - Gd * d0;
             float pd = 0.f, dd = 0.f;
