@@ -661,7 +661,10 @@ def main():
     clocks = sampler.summary() if sampler else None
 
     # per-launch device time of the library calls, live over a second (eager) pass of the same steps
+    # (the device is first parked on a ~2 ms spin so that the whole step is already queued when it starts executing:
+    # otherwise each event pair also brackets the host's submission gap, which is 15-20 us per call from Python)
     def step_eager(i):
+        torch.cuda._sleep(4_000_000)
         run_step(loss_mod, sets[i % N_INPUT_SETS], n_src)
     eager_steps = min(args.steps, 50)
     l0 = _timing.LAUNCH_COUNT

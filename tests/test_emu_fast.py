@@ -74,10 +74,16 @@ def test_fast_pair_loss_vs_golden(case, tag):
     assert rel_l2(g_pose, g.t("pair_%s/g_pose" % tag)) < 1e-3
 
 
-@pytest.mark.parametrize("hw", [(37, 150), (33, 65), (2, 2), (3, 64), (64, 3), (31, 129)])
-def test_fast_multi_group_partial_tiles_and_odd_sizes(hw):
-    """Forward + inverse direction in one launch on sizes that are not multiples of the 64x32 / 64x16 tiles (odd
-    heights exercise the padded last pair-row of the workspace), against the oracle."""
+@pytest.mark.parametrize("hw,tile_h", [((37, 150), None), ((33, 65), None), ((2, 2), None), ((3, 64), None), ((64, 3), None),
+                                       ((31, 129), None), ((37, 150), 16), ((37, 150), 24), ((49, 65), 24), ((37, 150), 32)])
+def test_fast_multi_group_partial_tiles_and_odd_sizes(hw, tile_h, monkeypatch):
+    """Forward + inverse direction in one launch on sizes that are not multiples of the 64 x {16, 24, 32} tiles (odd
+    heights exercise the last pixel pair of a column), against the oracle; every tile height the host may pick
+    (TCSFM_FAST_FH pins it, None = the wave-count rule)."""
+    if tile_h is None:
+        monkeypatch.delenv("TCSFM_FAST_FH", raising=False)
+    else:
+        monkeypatch.setenv("TCSFM_FAST_FH", str(tile_h))
     h, w = hw
     fr = synth.make_frames(2, h, w, seed=9)
     cfg = goldens.FULL_CFG
