@@ -477,6 +477,23 @@ def train_measure(R, steps, warm, wl_name="train376x4"):
     return out
 
 
+def h2d_ceiling(dev, mbytes=256, reps=4):
+    """Best-of-`reps` pinned host -> device bandwidth of one large copy (GB/s): the host link's ceiling the end-to-end
+    number is read against."""
+    src = torch.empty(mbytes << 20, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(mbytes << 20, dtype=torch.uint8, device=dev)
+    best = 0.0
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, (mbytes << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
 def eager_cuda_measure(wl, sets, cfg, steps):
     """The reference's eager PyTorch path (the oracle's op-for-op restatement: the same ATen CUDA kernels in the same
     order, including mean_on_mask's host synchronisation) on the same B200 -- the bar a user of the reference sees."""
@@ -672,6 +689,9 @@ def main():
     with _timing.record(timer):
         R.timed(step_eager, eager_steps)
     ksum = timer.summary()
+    tie_fraction = None
+    if args.arith == "fast" and ops.LAST_TIE_COUNT is not None:      # near-ties of the min-reprojection re-evaluated exactly
+        tie_fraction = int(ops.LAST_TIE_COUNT) / float(wl["b"] * wl["h"] * wl["w"])
     if graphs is not None:       # launches inside a replayed graph are not seen by the Python counter
         launches = (_timing.LAUNCH_COUNT - l0) // eager_steps * args.steps
 
@@ -679,6 +699,7 @@ def main():
         step_e2e(i)
     e2e_steps = max(5, min(args.steps, 500))
     ms_e2e = R.timed(step_e2e, e2e_steps)
+    h2d_peak = h2d_ceiling(dev)
     # Opt-in end-to-end mode: the three frames cross the host link as uint8 (what the loader reads from disk) and are
     # converted on the device with the loader's own arithmetic (tcsfm_u8_to_float == custom_transforms.py:74, bit for
     # bit); disparities / poses / K stay fp32.  Same pipeline as above: copy of step i+1 overlaps compute of step i.
@@ -823,9 +844,10 @@ def main():
             "pairs_per_s": value * 2 * n_src, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                    "h2d_GBps_per_gpu": h2d / (ms_e2e / e2e_steps * 1e-3) / 1e9},
+                    "h2d_GBps_per_gpu": h2d / (ms_e2e / e2e_steps * 1e-3) / 1e9, "h2d_peak_GBps": h2d_peak},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "e2e_uint8_images": e2e_u8, "eager_cuda_baseline": eager_cuda, "other_arithmetic": other}
+            "e2e_uint8_images": e2e_u8, "eager_cuda_baseline": eager_cuda, "other_arithmetic": other,
+            "tie_fraction": tie_fraction}
     line.update(sub)
     emit(line)
 

@@ -21,6 +21,8 @@ ARITH_FLAGS = 0
 # and evaluates the 3x3 SSIM statistics at tolerance level (loss <= 1e-5, gradients <= 1e-4 of the reference).
 PAIR_ARITHMETIC = "exact"
 PAIR_ARITHMETICS = ("exact", "fast")
+# diagnostics: the device-side near-tie count ([1] int32) of the most recent fast-arithmetic frame loss
+LAST_TIE_COUNT = None
 
 
 def set_arithmetic(mode):
@@ -288,6 +290,8 @@ class FrameLossFn(torch.autograd.Function):
                 # tolerance-level diff values: the near-ties of the per-pixel min are re-decided with the exact arithmetic
                 min_sum, tie_list, tie_count = _raw.min_reduce_ties(lib(), diff[fwd_idx[0]], step * n_px, len(fwd_idx), n_px)
                 _raw.pair_tie_resolve(lib(), batch, fwd_idx, meta["w_l1"], meta["w_ssim"], flags, tie_list, tie_count)
+                global LAST_TIE_COUNT
+                LAST_TIE_COUNT = tie_count
             elif fwd_idx:
                 min_sum = _raw.min_reduce(lib(), diff[fwd_idx[0]], step * n_px, len(fwd_idx), n_px)
             cfg = _raw.make_frame_cfg([grp[0] for grp in groups], meta["w_inverse"], meta["w_depth"], n_px)

@@ -25,6 +25,7 @@ def timeit(fn, iters=40):
         fn(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(10_000_000)        # ~5 ms: every launch below is queued before the first one starts (no host gaps in the interval)
     e0.record()
     for i in range(iters):
         fn(i)
@@ -113,4 +114,35 @@ def f_smooth(i):
 
 
 report("smooth_fwd (get_smooth_loss)", timeit(f_smooth), 4 + 4 + 12)
+
+
+# PFT window reduction (optimizer.py:45-97): 2 sources, the five stacked [2*S*B',1,H,W] maps of one window minibatch
+from tcsfm_b200 import _cabi  # noqa: E402
+pb, ns = max(1, b // 4), 2
+maps = [[torch.rand(2 * ns * pb, 1, h, w, device=dev) for _ in range(5)] for _ in range(n_sets)]
+for m in maps:
+    m[1].round_()
+    m[3].round_()
+pflags = _cabi.PFT_AUTOMASK | _cabi.PFT_INVERSE | _cabi.PFT_DEPTH_CONSIST
+g_loss = torch.ones(1, device=dev)
+
+
+def f_pft(i):
+    return _raw.pft_reduce_fwd(L, *maps[i % n_sets], pb, ns, pflags, 0.14)
+
+
+pft_out = [f_pft(i) for i in range(n_sets)]
+
+
+def f_pft_bwd(i):
+    _, sums, kept = pft_out[i % n_sets]
+    return _raw.pft_reduce_bwd(L, kept, sums, g_loss, pb, ns, pflags, 0.14)
+
+
+# bytes per pixel of one map element: fwd reads diff, valid, weight of both halves + auto_err (fwd) + auto_mask (inv);
+# bwd reads the same and writes g_diff, g_weight
+npx_full, npx = npx, 2 * ns * pb * h * w
+report("pft_reduce_fwd (optimizer.py:45-86)", timeit(f_pft), 16)
+report("pft_reduce_bwd", timeit(f_pft_bwd), 16 + 8)
+npx = npx_full
 print(json.dumps({"shape": [b, h, w], "peak_GBps": peak, "rows": rows}, indent=1))
