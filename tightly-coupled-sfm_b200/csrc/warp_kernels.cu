@@ -10,7 +10,10 @@
 namespace tcsfm {
 
 constexpr int kWarpThreads = 256;
-constexpr int kWarpBwdPix = 4;
+#ifndef TCSFM_WARP_BWD_PIX
+#define TCSFM_WARP_BWD_PIX 4
+#endif
+constexpr int kWarpBwdPix = TCSFM_WARP_BWD_PIX;
 #ifndef TCSFM_WARP_BWD_BLOCKS
 #define TCSFM_WARP_BWD_BLOCKS 5     // latency bound (ncu: long scoreboard 60 %): 5 CTAs/SM at 48 registers beat 3 at 80 by 11 %
 #endif
@@ -80,14 +83,23 @@ warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int img_sc,
     const float* rdep_b = pin_pointer(ref_depth + (int64_t)b * n);
     const float* goimg_b = pin_pointer(g_oimg ? g_oimg + (int64_t)b * 3 * n : nullptr);
     const float* gostk_b = pin_pointer(g_ostack ? g_ostack + (int64_t)b * 6 * n + (int64_t)3 * n : nullptr);
-    // kWarpBwdPix pixels per thread: the 12-value block reduction and the camera loads are amortised
+    // kWarpBwdPix pixels per thread: the 12-value block reduction and the camera loads are amortised.  The depth heads
+    // the dependent chain depth -> projection -> tap addresses -> gathers: the next pixel's is requested one iteration ahead.
+    const int pix0 = blockIdx.x * kWarpBwdPix * kWarpThreads + threadIdx.x;
+    float dep_next = pix0 < n ? __ldg(dep_b + pix0) : 1.0f;
 #pragma unroll kWarpBwdUnroll
     for (int k = 0; k < kWarpBwdPix; ++k) {
-        const int pix = (blockIdx.x * kWarpBwdPix + k) * kWarpThreads + threadIdx.x;
+        const int pix = pix0 + k * kWarpThreads;
         if (pix >= n) break;
+#ifdef TCSFM_WARP_BWD_NO_PREFETCH      // (tuning builds)
+        const float dep = __ldg(dep_b + pix);
+#else
+        const float dep = dep_next;
+        if (k + 1 < kWarpBwdPix) dep_next = (pix + kWarpThreads < n) ? __ldg(dep_b + pix + kWarpThreads) : 1.0f;
+#endif
         const int v = pix / A.W, u = pix - v * A.W;
         WarpPt p;
-        warp_point<F>(c, A, u, v, __ldg(dep_b + pix), p);
+        warp_point<F>(c, A, u, v, dep, p);
         const TapIdx ti = make_taps(p, A.H, A.W);
         float g_ix = 0.f, g_iy = 0.f;
         if (goimg_b || gostk_b) {
