@@ -27,7 +27,7 @@ for arith in fast exact; do
     TCSFM_ARITH=$arith ncu --set full --clock-control none --import-source on -k regex:pair_ -c 2 -s 2 -o $out/prof_$arith -f \
       python tools/profile_step.py 2 1 > $out/ncu_full_$arith.log 2>&1
   ncu -i $out/prof_$arith.ncu-rep --page raw --csv > $out/prof_${arith}_raw.csv 2>/dev/null
-  ncu -i $out/prof_$arith.ncu-rep --page source --csv --print-source cuda > $out/prof_${arith}_src.csv 2>/dev/null
+  ncu -i $out/prof_$arith.ncu-rep --page source --csv --print-source cuda,sass > $out/prof_${arith}_src.csv 2>/dev/null
 done
 # the PFT hot path proper (leaf disparities, no depth network): launch list of three epochs
 python tools/profile_pft_hotpath.py 3 > $out/pft_hot_plain.log 2>&1 && \
