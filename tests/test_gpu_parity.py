@@ -423,6 +423,21 @@ def test_pft_window_cuda_graph_matches_eager():
     assert torch.allclose(graph["losses"], eager["losses"], rtol=1e-4, atol=0), (graph["losses"], eager["losses"])
 
 
+@pytest.mark.parametrize("depth_range", [synth.KITTI_DEPTH_RANGE, (0.1, 10.0)])
+def test_disp_to_depth_vs_eager_cuda(depth_range):
+    """disp_to_depth (utils/learning_helpers.py:77-86) as called per frame and epoch by PFT: both outputs bit-identical
+    to the eager expression, gradient (through the depth and through the scaled disparity) within 1e-6."""
+    fr = frames(6, 192, 640, 0.01, depth_range, seed=8)
+    d_ref, d_got = leaf(fr["disps"][0]), leaf(fr["disps"][0])
+    s_ref, z_ref = O.disp_to_depth(d_ref, *depth_range)
+    s_got, z_got = losses.disp_to_depth(d_got, *depth_range)
+    assert torch.equal(s_ref, s_got) and torch.equal(z_ref, z_got)
+    g = torch.randn_like(z_ref)
+    (z_ref * g + 0.3 * s_ref).sum().backward()
+    (z_got * g + 0.3 * s_got).sum().backward()
+    assert rel_l2(d_got.grad, d_ref.grad) < 1e-6, rel_l2(d_got.grad, d_ref.grad)
+
+
 @pytest.mark.parametrize("shape", [(8, 192, 640), (3, 50, 77)])
 def test_smooth_loss_vs_eager_cuda(shape):
     """get_smooth_loss (losses.py:43-61): value within 1e-5 of eager PyTorch; gradient within 1e-4

@@ -33,7 +33,12 @@ def disp_to_depth(disp, min_depth, max_depth):
     min_disp = 1 / max_depth
     max_disp = 1 / min_depth
     scaled_disp = min_disp + (max_disp - min_disp) * disp
-    depth = 1 / scaled_disp
+    if torch.is_tensor(disp) and disp.is_cuda and disp.dtype == torch.float32:
+        # the reciprocal and its adjoint as one launch each way (PFT calls this for every frame of every epoch,
+        # optimization_experiments/optimizer.py:245); same bits as 1 / scaled_disp
+        depth = ops.DispToDepthFn.apply(disp, min_disp, max_disp)
+    else:
+        depth = 1 / scaled_disp
     return scaled_disp, depth
 
 

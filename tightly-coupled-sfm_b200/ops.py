@@ -217,6 +217,27 @@ class PairLossFn(torch.autograd.Function):
         return tuple(grads)
 
 
+class DispToDepthFn(torch.autograd.Function):
+    """depth = 1 / (min_disp + (max_disp - min_disp) * disp) (utils/learning_helpers.py:77-86) as one launch
+    each way; bit-identical to the eager expression (rounded product, rounded sum, IEEE reciprocal)."""
+
+    @staticmethod
+    def forward(ctx, disp, min_disp, max_disp):
+        _require_cuda(disp)
+        with _guard(disp):
+            depth = _raw.disp_to_depth_fwd(lib(), [disp], min_disp, max_disp - min_disp)[0]
+        ctx.save_for_backward(depth)
+        ctx.disp_range = max_disp - min_disp
+        return depth
+
+    @staticmethod
+    def backward(ctx, g_depth):
+        (depth,) = ctx.saved_tensors
+        with _guard(depth):
+            g = _raw.disp_to_depth_bwd(lib(), [g_depth.contiguous()], [depth], ctx.disp_range)[0]
+        return g, None, None
+
+
 class PoseProjFn(torch.autograd.Function):
     """pose [N,6] (multiplied by `sign`), K [Bk,3,3] -> K @ [Rx Ry Rz | t] as [N,3,4]
     (csrc/frame_kernels.cu); one launch forward, one backward."""
