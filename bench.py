@@ -76,7 +76,7 @@ DEFAULT_ARITH = "fast"
 N_INPUT_SETS = 8      # rotating input sets: 8 x ~47 MB > 126 MB of L2, so no step finds its inputs in L2
 
 
-def make_inputs(wl, seed, device, pin=False):
+def make_inputs(wl, seed, device, pin=False, slab=False):
     from tcsfm_b200 import synth
     kitti = wl["h"] in (192, 376)
     rng = synth.KITTI_DEPTH_RANGE if kitti else synth.SCANNET_DEPTH_RANGE
@@ -93,15 +93,21 @@ def make_inputs(wl, seed, device, pin=False):
     base[1, 1] *= 1.0 + 0.002 * (seed % 3)
     base[0, 2] += 0.25 * (seed % 4)
     fr = synth.make_frames(wl["b"], wl["h"], wl["w"], n_src=wl["n_src"], seed=seed, depth_range=rng, intrinsics=base)
-    flat = {"target": fr["target"], "K": fr["K"]}
+    flat = {"target": fr["target"]}                 # the frames first: they form one contiguous region of a slab
     for j in range(wl["n_src"]):
         flat["source%d" % j] = fr["sources"][j]
+    flat["K"] = fr["K"]
+    for j in range(wl["n_src"]):
         flat["pose%d" % j] = fr["poses"][j]
         flat["pose_inv%d" % j] = fr["poses_inv"][j]
     for j in range(1 + wl["n_src"]):
         flat["disp%d" % j] = fr["disps"][j]
         for sc in range(1, wl.get("scales", 1)):          # lower-resolution disparities of the other scales
             flat["disp%d_s%d" % (j, sc)] = torch.nn.functional.avg_pool2d(fr["disps"][j], 2 ** sc, ceil_mode=True)
+    if slab:
+        # one contiguous buffer per minibatch (dataformat.pack_slab): the end-to-end arm moves it with a single copy
+        from tcsfm_b200 import dataformat
+        return dataformat.pack_slab(flat, device=device, pin=pin)
     if pin:
         return {k: v.pin_memory() for k, v in flat.items()}
     return {k: v.to(device) for k, v in flat.items()}
@@ -477,7 +483,7 @@ def train_measure(R, steps, warm, wl_name="train376x4"):
     return out
 
 
-def h2d_ceiling(dev, mbytes=256, reps=4):
+def h2d_ceiling(dev, mbytes=512, reps=6):
     """Best-of-`reps` pinned host -> device bandwidth of one large copy (GB/s): the host link's ceiling the end-to-end
     number is read against."""
     src = torch.empty(mbytes << 20, dtype=torch.uint8).pin_memory()
@@ -602,8 +608,12 @@ def main():
     loss_cfg = dict(LOSS_CFG, num_scales=wl.get("scales", 1), min_depth=rng[0], max_depth=rng[1], **flags_cfg)
     loss_mod = losses.Compute_Loss(loss_cfg)
     n_src = wl["n_src"]
-    sets = [make_inputs(wl, 100 * rank + s, dev) for s in range(N_INPUT_SETS)]
-    host_sets = [make_inputs(wl, 100 * rank + s, dev, pin=True) for s in range(2)]
+    # sets 0 and 1 double as the device-side staging buffers of the end-to-end arm: each is one slab, mirrored by a
+    # pinned host slab of the same layout
+    dev_slabs = [make_inputs(wl, 100 * rank + s, dev, slab=True) for s in range(2)]
+    sets = [d[1] for d in dev_slabs] + [make_inputs(wl, 100 * rank + s, dev) for s in range(2, N_INPUT_SETS)]
+    host_slabs = [make_inputs(wl, 100 * rank + s, dev, pin=True, slab=True) for s in range(2)]
+    host_sets = [h[1] for h in host_slabs]
 
     # The resident-input arm replays one captured CUDA graph per input set (the step has no host-side control flow:
     # the mean-on-mask threshold is decided on the device, K^-1 is computed inside the step without a host check), so
@@ -654,8 +664,7 @@ def main():
         k = i % 2
         with torch.cuda.stream(copy_stream), torch.no_grad():
             copy_stream.wait_event(e2e["compute_done"][k])          # buffer k is free again
-            for name, src in h.items():
-                e2e["bufs"][k][name].copy_(src, non_blocking=True)
+            dev_slabs[k][0].copy_(host_slabs[i % 2][0], non_blocking=True)    # the whole minibatch: one copy
             e2e["h2d_done"][k].record(copy_stream)
         main = torch.cuda.current_stream()
         main.wait_event(e2e["h2d_done"][k])
@@ -707,19 +716,21 @@ def main():
     if e2e is not None:
         from tcsfm_b200 import dataformat
         img_keys = [k for k in host_sets[0] if k == "target" or k.startswith("source")]
-        host_u8 = [{k: (h[k] * 255).round().to(torch.uint8).pin_memory() for k in img_keys} for h in host_sets]
-        dev_u8 = [{k: torch.empty(host_u8[0][k].shape, dtype=torch.uint8, device=dev) for k in img_keys} for _ in range(2)]
+        # the frames are the leading region of the slab (make_inputs puts them first; their element counts are multiples
+        # of the slab alignment): one uint8 copy + one conversion launch for all of them, one fp32 copy for the rest
+        n_img = sum(host_sets[0][k].numel() for k in img_keys)
+        first_other = next(k for k in host_sets[0] if k not in img_keys)
+        assert (host_sets[0][first_other].data_ptr() - host_slabs[0][0].data_ptr()) // 4 == n_img
+        host_u8 = [(h[0][:n_img] * 255).round().to(torch.uint8).pin_memory() for h in host_slabs]
+        dev_u8 = [torch.empty(n_img, dtype=torch.uint8, device=dev) for _ in range(2)]
 
         def step_e2e_u8(i):
-            h, k = host_sets[i % 2], i % 2
+            k = i % 2
             with torch.cuda.stream(copy_stream), torch.no_grad():
                 copy_stream.wait_event(e2e["compute_done"][k])
-                for name, src in h.items():
-                    if name in img_keys:
-                        dev_u8[k][name].copy_(host_u8[i % 2][name], non_blocking=True)
-                        dataformat.images_from_uint8(dev_u8[k][name], e2e["bufs"][k][name])
-                    else:
-                        e2e["bufs"][k][name].copy_(src, non_blocking=True)
+                dev_u8[k].copy_(host_u8[i % 2], non_blocking=True)
+                dataformat.images_from_uint8(dev_u8[k], dev_slabs[k][0][:n_img])
+                dev_slabs[k][0][n_img:].copy_(host_slabs[i % 2][0][n_img:], non_blocking=True)
                 e2e["h2d_done"][k].record(copy_stream)
             main = torch.cuda.current_stream()
             main.wait_event(e2e["h2d_done"][k])
@@ -733,8 +744,7 @@ def main():
         for i in range(min(args.warmup, 5)):
             step_e2e_u8(i)
         ms_u8 = R.timed(step_e2e_u8, e2e_steps)
-        h2d_u8 = sum(v.numel() for v in host_u8[0].values()) + \
-            sum(v.numel() * v.element_size() for k_, v in host_sets[0].items() if k_ not in img_keys)
+        h2d_u8 = n_img + (host_slabs[0][0].numel() - n_img) * 4
         e2e_u8 = {"value": wl["b"] * world * e2e_steps / (ms_u8 / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d_u8,
                   "d2h_bytes_per_step": 4, "ms_per_step": ms_u8 / e2e_steps, "steps": e2e_steps,
                   "note": "opt-in: frames cross the host link as uint8 and are converted on the device exactly like the "
@@ -805,7 +815,7 @@ def main():
     frames = wl["b"] * world
     value = frames * args.steps / (ms_total / 1e3)
     e2e_value = frames * e2e_steps / (ms_e2e / 1e3)
-    h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+    h2d = host_slabs[0][0].numel() * host_slabs[0][0].element_size()      # the slab that is copied, padding included
     npx = wl["h"] * wl["w"]
     pairs = 2 * n_src * wl["b"] * wl.get("scales", 1)
     # algorithmic bytes per pixel per pair (SURVEY.md §8d / DESIGN.md): fwd 32 R + 8 W, bwd 36 R + 8 W

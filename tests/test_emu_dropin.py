@@ -544,3 +544,24 @@ def test_images_from_uint8_matches_the_loader_conversion(emu_ops):
     assert torch.equal(dataformat.images_from_uint8(img[:, :, 1:, 3:]), img[:, :, 1:, 3:].float() / 255)
     with pytest.raises(TypeError):
         dataformat.images_from_uint8(out)
+
+
+def test_pack_slab_views_alias_one_buffer():
+    """dataformat.pack_slab: the minibatch as one contiguous buffer (one host->device copy), views 256-byte aligned."""
+    from tcsfm_b200 import dataformat, synth
+    fr = synth.make_frames(2, 10, 14, seed=1)
+    tensors = {"target": fr["target"], "K": fr["K"], "pose0": fr["poses"][0], "disp0": fr["disps"][0]}
+    slab, views = dataformat.pack_slab(tensors)
+    assert slab.dim() == 1 and slab.dtype == torch.float32
+    for name, t in tensors.items():
+        v = views[name]
+        assert v.shape == t.shape and torch.equal(v, t)
+        off = (v.data_ptr() - slab.data_ptr()) // 4
+        assert off % 64 == 0 and 0 <= off and off + t.numel() <= slab.numel()
+    slab.zero_()
+    assert all(float(v.abs().sum()) == 0.0 for v in views.values())          # views alias the slab
+    other, views2 = dataformat.pack_slab(tensors)
+    slab.copy_(other)                                                         # "one copy" moves every tensor
+    assert all(torch.equal(views[k], tensors[k]) for k in tensors)
+    with pytest.raises(TypeError):
+        dataformat.pack_slab({"a": torch.zeros(3), "b": torch.zeros(3, dtype=torch.int32)})
