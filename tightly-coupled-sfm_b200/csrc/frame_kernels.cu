@@ -127,24 +127,68 @@ __global__ void pose_proj_bwd_kernel(const float* __restrict__ pose, float sign,
 // (mul by scalar, add scalar, reciprocal).  Backward: g_disp = -g_depth * depth^2 * (max_disp - min_disp).
 struct MapPtrs { const float* in[4]; const float* aux[4]; float* out[4]; int count; };
 
+// kVec = 4: 16-byte accesses (n % 4 == 0 and every pointer 16-byte aligned, checked by the launcher); the loads of all
+// maps of a thread are in flight before the first store.
+template <int kVec>
 __global__ void __launch_bounds__(256)
 disp_to_depth_fwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float min_disp, float range) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kVec;
     if (i >= n) return;
-    for (int k = 0; k < M.count; ++k) {
-        const float scaled = __fadd_rn(__fmul_rn(__ldg(M.in[k] + i), range), min_disp);
-        M.out[k][i] = __frcp_rn(scaled);
-    }
+    float v[4][kVec];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < M.count) {
+            if (kVec == 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(M.in[k] + i));
+                v[k][0] = q.x; v[k][1 % kVec] = q.y; v[k][2 % kVec] = q.z; v[k][3 % kVec] = q.w;
+            } else {
+                v[k][0] = __ldg(M.in[k] + i);
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < M.count) {
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) v[k][j] = __frcp_rn(__fadd_rn(__fmul_rn(v[k][j], range), min_disp));
+            if (kVec == 4) *reinterpret_cast<float4*>(M.out[k] + i) = make_float4(v[k][0], v[k][1 % kVec], v[k][2 % kVec], v[k][3 % kVec]);
+            else M.out[k][i] = v[k][0];
+        }
 }
 
+template <int kVec>
 __global__ void __launch_bounds__(256)
 disp_to_depth_bwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float range) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kVec;
     if (i >= n) return;
-    for (int k = 0; k < M.count; ++k) {
-        const float d = __ldg(M.aux[k] + i);            // the depth computed by the forward
-        M.out[k][i] = -__ldg(M.in[k] + i) * d * d * range;
-    }
+    float g[4][kVec], d[4][kVec];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < M.count) {
+            if (kVec == 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(M.in[k] + i));
+                const float4 r = __ldg(reinterpret_cast<const float4*>(M.aux[k] + i));       // the depth computed by the forward
+                g[k][0] = q.x; g[k][1 % kVec] = q.y; g[k][2 % kVec] = q.z; g[k][3 % kVec] = q.w;
+                d[k][0] = r.x; d[k][1 % kVec] = r.y; d[k][2 % kVec] = r.z; d[k][3 % kVec] = r.w;
+            } else {
+                g[k][0] = __ldg(M.in[k] + i);
+                d[k][0] = __ldg(M.aux[k] + i);
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < M.count) {
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) g[k][j] = -g[k][j] * d[k][j] * d[k][j] * range;
+            if (kVec == 4) *reinterpret_cast<float4*>(M.out[k] + i) = make_float4(g[k][0], g[k][1 % kVec], g[k][2 % kVec], g[k][3 % kVec]);
+            else M.out[k][i] = g[k][0];
+        }
+}
+
+static bool maps_vectorisable(const MapPtrs& M, int64_t n) {
+    if (n % 4) return false;
+    for (int k = 0; k < M.count; ++k)
+        if (((uintptr_t)M.in[k] | (uintptr_t)M.out[k] | (uintptr_t)M.aux[k]) & 15) return false;
+    return true;
 }
 
 // The same with the nearest-neighbour upsample of the lower pyramid scales folded in
@@ -362,7 +406,10 @@ extern "C" int tcsfm_disp_to_depth_fwd(const float* const* disp, float* const* d
     memset(&M, 0, sizeof(M));
     M.count = count;
     for (int k = 0; k < count; ++k) { M.in[k] = disp[k]; M.out[k] = depth[k]; }
-    TCSFM_LAUNCH(disp_to_depth_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, M, n, min_disp, range);
+    if (maps_vectorisable(M, n))
+        TCSFM_LAUNCH(disp_to_depth_fwd_kernel<4>, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, stream, M, n, min_disp, range);
+    else
+        TCSFM_LAUNCH(disp_to_depth_fwd_kernel<1>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, M, n, min_disp, range);
     return check_launch("tcsfm_disp_to_depth_fwd");
 }
 
@@ -373,7 +420,10 @@ extern "C" int tcsfm_disp_to_depth_bwd(const float* const* g_depth, const float*
     memset(&M, 0, sizeof(M));
     M.count = count;
     for (int k = 0; k < count; ++k) { M.in[k] = g_depth[k]; M.aux[k] = depth[k]; M.out[k] = g_disp[k]; }
-    TCSFM_LAUNCH(disp_to_depth_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, M, n, range);
+    if (maps_vectorisable(M, n))
+        TCSFM_LAUNCH(disp_to_depth_bwd_kernel<4>, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, stream, M, n, range);
+    else
+        TCSFM_LAUNCH(disp_to_depth_bwd_kernel<1>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, M, n, range);
     return check_launch("tcsfm_disp_to_depth_bwd");
 }
 
