@@ -801,3 +801,24 @@ def test_fast_randomised_sweep_vs_eager_cuda(fast_arith):
         assert abs(res[1][0] - res[0][0]) <= 1e-5 * abs(res[0][0]), (it, b, h, w, res[1][0], res[0][0])
         for j in range(3):
             assert rel_l2(res[1][1][j], res[0][1][j]) < 1e-4, (it, b, h, w, j, rel_l2(res[1][1][j], res[0][1][j]))
+
+
+def test_graphed_train_step_matches_eager():
+    """training.FlatGradTrainer: forward+backward and Adam replayed as CUDA graphs give the losses and parameters of the
+    eager run_train_step on the same sequence of minibatches; building the trainer does not change the parameters."""
+    from tcsfm_b200 import training
+    cfg = training.default_config(num_scales=2, iterations=2, full_profile=True)
+    data = [synth.make_frames(2, 96, 160, seed=40 + s, device=DEV) for s in range(3)]
+    step_a, optim_a = training.make_step(cfg, seed=1, device=DEV, padded=False)
+    step_b, optim_b = training.make_step(cfg, seed=1, device=DEV, padded=False, capturable=True)
+    trainer = training.FlatGradTrainer(step_b, optim_b, data[0])
+    for p, q in zip(step_a.parameters(), step_b.parameters()):
+        assert torch.equal(p, q)
+    for fr in data:
+        ta = training.run_train_step(step_a, optim_a, fr)
+        tb = trainer.run(fr).clone()
+        assert torch.allclose(ta, tb, rtol=2e-5, atol=0), (ta, tb)
+    # (Adam's first updates are lr * sign-like: a gradient that rounds differently near zero moves a single weight by
+    # up to 2 lr, so the parameters are compared in the mean)
+    for p, q in zip(step_a.parameters(), step_b.parameters()):
+        assert float((p - q).abs().mean()) < 2e-5, float((p - q).abs().mean())

@@ -125,3 +125,61 @@ def test_ddp_two_ranks_average_the_sub_batch_gradients(tmp_path, emulated):
     for g, a, b in zip(ddp_grads, singles[0], singles[1]):
         want = 0.5 * (a + b)
         assert rel_l2(g, want) < 1e-5, rel_l2(g, want)
+
+
+def test_flat_grad_trainer_matches_the_plain_step(emulated):
+    """FlatGradTrainer (eager form of the CUDA-graphed step): same loss, same gradients, same Adam update as
+    run_train_step -- the gradients live in one flat buffer."""
+    from tcsfm_b200 import training
+    cfg = _config()
+    fr = _frames(5)
+    step_a, optim_a = training.make_step(cfg, seed=3, padded=False)
+    total_a = training.run_train_step(step_a, optim_a, fr)
+    step_b, optim_b = training.make_step(cfg, seed=3, padded=False)
+    trainer = training.FlatGradTrainer(step_b, optim_b, fr, use_graph=False)
+    total_b = trainer.run(fr)
+    assert torch.allclose(total_a, total_b, rtol=1e-6, atol=0)
+    for p, q in zip(step_a.parameters(), step_b.parameters()):
+        assert q.grad.data_ptr() >= trainer.flat.data_ptr() and q.grad.data_ptr() < trainer.flat.data_ptr() + 4 * trainer.flat.numel()
+        if p.grad is not None:
+            assert rel_l2(q.grad, p.grad) < 1e-6
+        assert torch.allclose(p, q, rtol=1e-6, atol=1e-9)
+    # a second step on other frames reuses the static buffers
+    total_b2 = trainer.run(_frames(6))
+    total_a2 = training.run_train_step(step_a, optim_a, _frames(6))
+    assert torch.allclose(total_a2, total_b2, rtol=1e-5, atol=0)
+
+
+def _flat_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    _use_emulator()
+    from tcsfm_b200 import training
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    step, optim = training.make_step(_config(), seed=3, padded=False)
+    fr = _frames(10 + rank)
+    trainer = training.FlatGradTrainer(step, optim, fr, group=dist.group.WORLD, use_graph=False)
+    trainer.run(fr)
+    if rank == 0:
+        torch.save([p.grad.clone() for p in step.parameters()], out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_grad_trainer_two_ranks_average_the_sub_batch_gradients(tmp_path, emulated):
+    """The one collective of the graphed data-parallel step: a single all-reduce (mean) of the flat gradient buffer."""
+    from tcsfm_b200 import training
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out_path = str(tmp_path / "flat_grads.pt")
+    mp.spawn(_flat_worker, args=(2, port, out_path), nprocs=2, join=True)
+    got = torch.load(out_path)
+    singles = []
+    for rank in range(2):
+        step, optim = training.make_step(_config(), seed=3, padded=False)
+        training.run_train_step(step, optim, _frames(10 + rank))
+        singles.append([p.grad if p.grad is not None else torch.zeros_like(p) for p in step.parameters()])
+    for g, a, b in zip(got, singles[0], singles[1]):
+        want = 0.5 * (a + b)
+        assert rel_l2(g, want) < 1e-5 or float((g - want).abs().max()) < 1e-12, rel_l2(g, want)

@@ -118,12 +118,13 @@ def default_config(num_scales=1, iterations=4, depth_range=synth.KITTI_DEPTH_RAN
             "l_pose_consist": True, "l_pose_consist_weight": 5, "iterations": iterations}
 
 
-def make_step(config, seed=0, device="cpu", padded=True, backend=Backend, lr=9e-4):
-    """(TrainStep, Adam) with seeded stand-in networks; `padded` = reference-sized parameter volume."""
+def make_step(config, seed=0, device="cpu", padded=True, backend=Backend, lr=9e-4, capturable=False):
+    """(TrainStep, Adam) with seeded stand-in networks; `padded` = reference-sized parameter volume;
+    `capturable`: Adam keeps its step counter on the device so that `optim.step()` can live in a CUDA graph."""
     depth = StandInDepthNet(seed, config['num_scales'], n_params=REFERENCE_DEPTH_PARAMS if padded else 0)
     pose = StandInPoseNet(seed, n_params=REFERENCE_POSE_PARAMS if padded else 0)
     step = TrainStep(depth, pose, config, backend).to(device)
-    optim = torch.optim.Adam(step.parameters(), lr=lr)                                   # run_mono_training.py:155
+    optim = torch.optim.Adam(step.parameters(), lr=lr, capturable=capturable)            # run_mono_training.py:155
     return step, optim
 
 
@@ -146,3 +147,94 @@ def run_train_step(model, optim, frames, sync=True):
         total.sum().backward()
     optim.step()
     return total.detach()
+
+
+class FlatGradTrainer:
+    """The same optimisation step with the host taken out of it: every parameter's gradient is a view of ONE flat
+    buffer, forward + backward are captured as one CUDA graph and the Adam update as a second one; between the two
+    replays the data-parallel form issues a single NCCL all-reduce (mean) of the flat buffer -- still the only
+    collective of the mode, but one launch over the whole 62.8 MB instead of DDP's per-bucket calls interleaved with a
+    host-launch-bound backward.  The eager step launches ~1 200 kernels from Python and is bound by that; the replayed
+    step is bound by the device.
+
+    `use_graph=False` runs the identical sequence eagerly (CPU / gloo tests, debugging).  The networks must not
+    change shape between steps and the frames must keep the shapes of `example` (static input buffers)."""
+
+    def __init__(self, step, optim, example, group=None, use_graph=True, warmup=3):
+        self.step, self.optim, self.group = step, optim, group
+        self.params = [p for p in step.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.static = {"target": example["target"].clone(), "sources": [t.clone() for t in example["sources"]],
+                       "K": example["K"].clone()}
+        self.total = None
+        self.graph_fb = self.graph_opt = None
+        if use_graph:
+            if dev.type != "cuda":
+                raise RuntimeError("FlatGradTrainer: CUDA graphs need CUDA parameters (use_graph=False for the eager form)")
+            # warm-up on a side stream (cuDNN plans, lazily created Adam state), then put parameters and optimizer
+            # state back IN PLACE -- the graphs hold their addresses -- so that building the trainer is not a step
+            saved_p = [p.detach().clone() for p in self.params]
+            saved_s = {id(t): t.clone() for st in self.optim.state.values() for t in st.values() if torch.is_tensor(t)}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._forward_backward()
+                    self._reduce()
+                    self.optim.step()
+            torch.cuda.current_stream().wait_stream(side)
+            with torch.no_grad():
+                for p, q in zip(self.params, saved_p):
+                    p.copy_(q)
+                for st in self.optim.state.values():
+                    for t in st.values():
+                        if torch.is_tensor(t):
+                            t.copy_(saved_s[id(t)]) if id(t) in saved_s else t.zero_()
+            torch.cuda.synchronize()
+            self.graph_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_fb):
+                self._forward_backward()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph_fb.pool()):
+                self.optim.step()
+
+    def _forward_backward(self):
+        self.flat.zero_()                       # the gradients accumulate in place into the views of `flat`
+        st = self.static
+        total = self.step(st["target"], *st["sources"], st["K"])
+        total.sum().backward()
+        self.total = total.detach()
+
+    def _reduce(self, sync=True):
+        if self.group is None or not sync:
+            return
+        import torch.distributed as dist
+        world = dist.get_world_size(self.group)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:                                   # gloo has no AVG
+            dist.all_reduce(self.flat, group=self.group)
+            self.flat.div_(world)
+
+    def run(self, frames, sync=True):
+        """One optimisation step on `frames` (synth.make_frames layout); returns the total loss (a static tensor that
+        the next step overwrites)."""
+        with torch.no_grad():
+            self.static["target"].copy_(frames["target"], non_blocking=True)
+            for dst, src in zip(self.static["sources"], frames["sources"]):
+                dst.copy_(src, non_blocking=True)
+            self.static["K"].copy_(frames["K"], non_blocking=True)
+        if self.graph_fb is not None:
+            self.graph_fb.replay()
+            self._reduce(sync)
+            self.graph_opt.replay()
+        else:
+            self._forward_backward()
+            self._reduce(sync)
+            self.optim.step()
+        return self.total
