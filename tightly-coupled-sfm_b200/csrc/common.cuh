@@ -124,6 +124,28 @@ __device__ __forceinline__ void async_copy16(float* smem_dst, const float* src, 
 #endif
 }
 
+// Warp-wide sums of N <= 16 per-thread values with 16 shuffles instead of 5 N: at every butterfly stage a lane keeps
+// one half of its values and hands the other half to its partner, so the number of live values halves with the
+// distance.  On return v[0] of lane L holds the warp total of value index ((L >> 1) & 15) (both lanes of a pair hold it).
+template <int N>
+__device__ __forceinline__ float warp_sum_transposed(const float (&part)[N], int lane) {
+    static_assert(N <= 16, "warp_sum_transposed handles at most 16 values");
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = i < N ? part[i] : 0.f;
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool upper = (lane & bit) != 0;           // this lane keeps the upper half of its live values
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = upper ? v[half + i] : v[i];
+            const float send = upper ? v[i] : v[half + i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // Block-wide sum of N per-thread partials -> one atomicAdd per value per block.
 // `red` is shared scratch of at least N * (threads/32) floats.  All threads of
 // the block must call this (it contains __syncthreads()).
@@ -131,10 +153,16 @@ template <int N>
 __device__ __forceinline__ void block_atomic_accumulate(const float (&part)[N], float* red, float* dst,
                                                         int tid, int nthreads) {
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    if (N > 4) {
+        const float s = warp_sum_transposed<N>(part, lane);
+        const int idx = (lane >> 1) & 15;
+        if (!(lane & 1) && idx < N) red[idx * nwarps + warp] = s;
+    } else {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        float s = warp_sum(part[i]);
-        if (lane == 0) red[i * nwarps + warp] = s;
+        for (int i = 0; i < N; ++i) {
+            float s = warp_sum(part[i]);
+            if (lane == 0) red[i * nwarps + warp] = s;
+        }
     }
     __syncthreads();
     if (tid < N) {

@@ -90,7 +90,7 @@ warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int img_sc,
 #pragma unroll kWarpBwdUnroll
     for (int k = 0; k < kWarpBwdPix; ++k) {
         const int pix = pix0 + k * kWarpThreads;
-        if (pix >= n) break;
+        if (pix >= n) continue;              // (not `break`: the warp stays provably converged for the reduction's shuffles)
 #ifdef TCSFM_WARP_BWD_NO_PREFETCH      // (tuning builds)
         const float dep = __ldg(dep_b + pix);
 #else
