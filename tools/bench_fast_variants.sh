@@ -12,7 +12,7 @@ name, defs = sys.argv[1], sys.argv[2]
 build.build_variant("build/libtcsfm_%s.so" % name, [d[2:] for d in defs.split(",") if d.startswith("-D")])
 PY
 done
-for lib in default build/libtcsfm_*.so; do
+for lib in default $(ls build/libtcsfm_*.so 2>/dev/null); do
   if [ "$lib" != default ]; then export TCSFM_B200_LIB=$PWD/$lib; else unset TCSFM_B200_LIB; fi
   for arith in ${ARITHS:-fast}; do
     python bench.py --steps 60 --warmup 10 --only loss --no-cpu-baseline --arith $arith > gpurun_out/bench_var.json 2> gpurun_out/bench_var.err || tail -3 gpurun_out/bench_var.err

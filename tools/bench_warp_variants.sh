@@ -12,7 +12,7 @@ name, defs = sys.argv[1], sys.argv[2]
 build.build_variant("build/libtcsfm_%s.so" % name, [d[2:] for d in defs.split(",") if d.startswith("-D")])
 PY
 done
-for lib in default build/libtcsfm_*.so; do
+for lib in default $(ls build/libtcsfm_*.so 2>/dev/null); do
   if [ "$lib" != default ]; then export TCSFM_B200_LIB=$PWD/$lib; else unset TCSFM_B200_LIB; fi
   python - "$lib" <<'PY'
 import sys
