@@ -289,6 +289,11 @@ def pft_measure(R, name, steps, warm, no_graph=False, sequence_frames=0):
     timer = _timing.KernelTimer()
     torch.cuda.synchronize()
     w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # (one untimed eager window first: the eager path's own lazy initialisations -- cuDNN plans of the stand-in network,
+    # allocator growth -- otherwise land in the interval)
+    pft_driver.optimize_window(depth_net, pose_net, data[0]["target"], data[0]["sources"], data[0]["K"], opts,
+                               wl["iterations"], rng, cuda_graph=False)
+    torch.cuda.synchronize()
     w0.record()
     with _timing.record(timer):
         pft_driver.optimize_window(depth_net, pose_net, data[0]["target"], data[0]["sources"], data[0]["K"], opts,
@@ -736,11 +741,12 @@ def main():
     if e2e is not None:
         from tcsfm_b200 import dataformat
         img_keys = [k for k in host_sets[0] if k == "target" or k.startswith("source")]
-        # the frames are the leading region of the slab (make_inputs puts them first; their element counts are multiples
-        # of the slab alignment): one uint8 copy + one conversion launch for all of them, one fp32 copy for the rest
-        n_img = sum(host_sets[0][k].numel() for k in img_keys)
+        # the frames are the leading region of the slab (make_inputs puts them first; the alignment padding between
+        # them is zero and converts to zero): one uint8 copy + one conversion launch for all of them, one fp32 copy for
+        # the rest
         first_other = next(k for k in host_sets[0] if k not in img_keys)
-        assert (host_sets[0][first_other].data_ptr() - host_slabs[0][0].data_ptr()) // 4 == n_img
+        n_img = (host_sets[0][first_other].data_ptr() - host_slabs[0][0].data_ptr()) // 4
+        assert list(host_sets[0])[:len(img_keys)] == img_keys and n_img >= sum(host_sets[0][k].numel() for k in img_keys)
         host_u8 = [(h[0][:n_img] * 255).round().to(torch.uint8).pin_memory() for h in host_slabs]
         dev_u8 = [torch.empty(n_img, dtype=torch.uint8, device=dev) for _ in range(2)]
 
@@ -779,9 +785,9 @@ def main():
     sub = {}
     if args.only is None and args.workload == "kitti":
         # driver-visible numbers for the other two modes of BASELINE.json's metric / configs 3-5
-        pft_steps = max(1, min(args.steps, 3))
-        sub["pft"] = pft_measure(R, "pft", pft_steps, 1, sequence_frames=1591)
-        sub["pft_scannet"] = pft_measure(R, "pft-scannet", pft_steps, 1)
+        pft_steps = max(1, min(args.steps, 6))
+        sub["pft"] = pft_measure(R, "pft", pft_steps, 2, sequence_frames=1591)
+        sub["pft_scannet"] = pft_measure(R, "pft-scannet", pft_steps, 2)
         sub["train_ddp" if world > 1 else "train"] = train_measure(R, max(3, min(args.steps, 10)), 3)
     other = None
     alt = "exact" if args.arith == "fast" else "fast"
