@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 11
+#define TCSFM_ABI_VERSION 12
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -252,6 +252,15 @@ int tcsfm_min_reduce_ties(const float* base, int64_t stride, int count, int64_t 
                           int* tie_list, int* tie_count, int capacity, void* stream);
 int tcsfm_pair_tie_resolve(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
                            float w_l1, float w_ssim, int flags, const int* tie_list, const int* tie_count, int capacity,
+                           void* stream);
+
+/* The two calls above as ONE launch (no tie list in global memory): every block takes the min of its pixels,
+ * keeps its near-ties in shared memory and re-evaluates them with the exact arithmetic right away.  out_sum [1]:
+ * sum over the B*H*W pixels of the min over the groups' diff_img (values as the forward produced them);
+ * tie_count [1]: number of pixels re-evaluated (diagnostics).  Replaces torch.min(reconstruction_errors, 1)[0]
+ * of losses.py:129-131 under the fast arithmetic. */
+int tcsfm_pair_min_resolve(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
+                           float w_l1, float w_ssim, int flags, float band, float* out_sum, int* tie_count,
                            void* stream);
 
 typedef struct tcsfm_frame_cfg {

@@ -192,3 +192,9 @@ def test_tie_resolver_restores_the_reference_routing():
         assert torch.equal(d_fast[j].flatten()[untouched], before[j].flatten()[untouched])
     assert torch.equal(torch.min(d_fast.reshape(2, -1), 0)[1], torch.min(d_exact.reshape(2, -1), 0)[1])
     assert abs(float(min_sum) - float(torch.min(before.reshape(2, -1), 0)[0].sum())) < 1e-3
+    # the same as ONE launch (tcsfm_pair_min_resolve: ties kept in shared memory, no list): identical maps, sum, count
+    batch2, d_fast2 = forward(cfg_flags(cfg))
+    min_sum2, tie_count2 = _raw.pair_min_resolve(emu(), batch2, [0, 1], 0.15, 0.85, cfg_flags(cfg))
+    assert int(tie_count2) == n_ties
+    assert torch.equal(d_fast2, d_fast)
+    assert abs(float(min_sum2) - float(min_sum)) < 1e-3

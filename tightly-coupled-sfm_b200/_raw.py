@@ -327,6 +327,21 @@ def pair_tie_resolve(lib, batch, group_ids, w_l1, w_ssim, flags, tie_list, tie_c
     _timing.count_launch()
 
 
+def pair_min_resolve(lib, batch, group_ids, w_l1, w_ssim, flags):
+    """min_reduce_ties + pair_tie_resolve as one launch: returns (sum [1] of the per-pixel min over the listed groups'
+    diff_img, tie_count int32 [1]); the groups' diff_img entries at the near-tie pixels now hold the exact
+    arithmetic's values."""
+    sub = (PairGroup * len(group_ids))(*[batch.arr[i] for i in group_ids])
+    out = torch.empty((1,), dtype=torch.float32, device=batch.device)
+    tie_count = torch.empty((1,), dtype=torch.int32, device=batch.device)
+    with _timing.launch("pair_min_resolve", batch.device.type == "cuda"):
+        rc = lib.tcsfm_pair_min_resolve(sub, len(group_ids), batch.b, batch.h, batch.w, w_l1, w_ssim, flags, TIE_BAND,
+                                        _ptr(out), _ptr(tie_count), batch.stream())
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return out, tie_count
+
+
 def make_frame_cfg(roles, w_inverse, w_depth, n_min_pixels):
     cfg = _cabi.FrameCfg()
     cfg.n_groups = len(roles)

@@ -713,19 +713,12 @@ pair_bwd_kernel(const __grid_constant__ PairLaunch L) {
 // avg_pool2d's row-major order from the shuffled values and lane 0 overwrites the group's diff_img entry.
 constexpr int kTieTasksPerBlock = 8;
 
+// One (pixel, group) task on the 16 lanes [seg, seg + 16) of a warp; every lane of the warp must call it (full-mask
+// shuffles), dead tasks (live = false) compute on pixel 0 and write nothing.
 template <int F>
-__global__ void __launch_bounds__(16 * kTieTasksPerBlock)
-tie_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, const int* __restrict__ tie_list,
-                   const int* __restrict__ tie_count, int capacity) {
-    const int n_tasks = min(__ldg(tie_count), capacity) * n_groups;
-    const int task0 = blockIdx.x * kTieTasksPerBlock;
-    if (task0 >= n_tasks) return;                          // the grid covers the list's capacity: most blocks are idle
-    const int sub = threadIdx.x & 15, task = task0 + (threadIdx.x >> 4);
-    const bool live = task < n_tasks;
-    const int e = live ? task / n_groups : 0, j = live ? task - e * n_groups : 0;
+__device__ __forceinline__ void resolve_tie(const PairLaunch& L, int j, int pix, int sub, bool live) {
     const Arith& A = L.A;
     const int H = A.H, W = A.W, n = H * W;
-    const int pix = __ldg(tie_list + e);
     const int b = pix / n, r = pix - b * n;
     const int y = r / W, x = r - y * W;
     const tcsfm_pair_group& g = L.g[j];
@@ -773,6 +766,66 @@ tie_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, const int
     }
     const float diff0 = mean3_of_sum<F>(esum, A);
     if (live && sub == 0) g.diff_img[pix] = need_depth ? __fmul_rn(diff0, __fsub_rn(1.0f, dd)) : diff0;
+}
+
+
+template <int F>
+__global__ void __launch_bounds__(16 * kTieTasksPerBlock)
+tie_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, const int* __restrict__ tie_list,
+                   const int* __restrict__ tie_count, int capacity) {
+    const int n_tasks = min(__ldg(tie_count), capacity) * n_groups;
+    const int task0 = blockIdx.x * kTieTasksPerBlock;
+    if (task0 >= n_tasks) return;                          // the grid covers the list's capacity: most blocks are idle
+    const int sub = threadIdx.x & 15, task = task0 + (threadIdx.x >> 4);
+    const bool live = task < n_tasks;
+    const int e = live ? task / n_groups : 0, j = live ? task - e * n_groups : 0;
+    resolve_tie<F>(L, j, __ldg(tie_list + e), sub, live);
+}
+
+// Per-pixel min over the competing forward groups (losses.py:129-132) and the exact re-evaluation of its near-ties in
+// ONE launch: a block takes the min of its 1024 pixels (sum -> out_sum), collects the pixels whose two best
+// candidates are closer than `band` (or involve a NaN) in shared memory and then re-evaluates exactly those with
+// the exact arithmetic, sixteen lanes per (pixel, group), overwriting the groups' diff_img entries before any
+// backward pass reads the routing.  The sum is the one of the values as the forward produced them.
+constexpr int kMinResolveThreads = 256, kMinResolvePix = 4;
+
+template <int F>
+__global__ void __launch_bounds__(kMinResolveThreads)
+min_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, int64_t n_total, float band,
+                   float* __restrict__ out_sum, int* __restrict__ tie_count) {
+    TCSFM_SHARED float red[kMinResolveThreads / 32];
+    TCSFM_SHARED int buf[kMinResolveThreads * kMinResolvePix];
+    TCSFM_SHARED int n_buf;
+    if (threadIdx.x == 0) n_buf = 0;
+    __syncthreads();
+    float part[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < kMinResolvePix; ++k) {
+        const int64_t i = ((int64_t)blockIdx.x * kMinResolvePix + k) * kMinResolveThreads + threadIdx.x;
+        if (i < n_total) {
+            float m = __ldg(L.g[0].diff_img + i), second = INFINITY;
+            bool odd = m != m;
+            for (int j = 1; j < n_groups; ++j) {
+                const float v = __ldg(L.g[j].diff_img + i);
+                odd = odd || v != v;
+                if (v < m) { second = m; m = v; }
+                else if (v < second) second = v;
+            }
+            part[0] += m;
+            if (n_groups > 1 && (odd || !(second - m >= band))) buf[atomicAdd(&n_buf, 1)] = (int)i;
+        }
+    }
+    __syncthreads();
+    const int ties = n_buf;
+    if (threadIdx.x == 0 && ties) atomicAdd(tie_count, ties);
+    const int n_tasks = ties * n_groups, sub = threadIdx.x & 15;
+    for (int t0 = 0; t0 < n_tasks; t0 += kMinResolveThreads / 16) {
+        const int task = t0 + (threadIdx.x >> 4);
+        const bool live = task < n_tasks;
+        const int e = live ? task / n_groups : 0, j = live ? task - e * n_groups : 0;
+        resolve_tie<F>(L, j, live ? buf[e] : 0, sub, live);
+    }
+    block_atomic_accumulate<1>(part, red, out_sum, threadIdx.x, kMinResolveThreads);
 }
 
 #ifndef TCSFM_HOST_EMU
@@ -936,4 +989,26 @@ extern "C" int tcsfm_pair_tie_resolve(const tcsfm_pair_group* groups, int n_grou
     dim3 grid((unsigned)((tasks + kTieTasksPerBlock - 1) / kTieTasksPerBlock)), block(16 * kTieTasksPerBlock);
     TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(tie_resolve_kernel<F>, grid, block, 0, stream, L, n_groups, tie_list, tie_count, capacity));
     return check_launch("tcsfm_pair_tie_resolve");
+}
+
+/* tcsfm_min_reduce_ties + tcsfm_pair_tie_resolve as one launch (no tie list in global memory): out_sum [1] = the sum
+ * over the B*H*W pixels of the min over the groups' diff_img, tie_count [1] = the number of pixels re-evaluated. */
+extern "C" int tcsfm_pair_min_resolve(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
+                                      float w_l1, float w_ssim, int flags, float band, float* out_sum, int* tie_count,
+                                      void* stream) {
+    if (!groups || n_groups <= 0 || n_groups > kMaxGroups) { set_error("tcsfm_pair_min_resolve: 1..%d groups", kMaxGroups); return 1; }
+    if (!out_sum || !tie_count) { set_error("tcsfm_pair_min_resolve: null output"); return 1; }
+    PairLaunch L;
+    memset(&L, 0, sizeof(L));
+    if (int rc = fill_launch(L, groups, n_groups, B, H, W, w_l1, w_ssim, flags & ~TCSFM_ARITH_FAST, "tcsfm_pair_min_resolve", false)) return rc;
+    for (int i = 0; i < n_groups; ++i)
+        if (!L.g[i].diff_img) { set_error("tcsfm_pair_min_resolve: group %d has no diff_img", i); return 1; }
+    const int64_t n_total = (int64_t)B * H * W;
+    if (n_total >= ((int64_t)1 << 31)) { set_error("tcsfm_pair_min_resolve: more than 2^31 pixels"); return 1; }
+    cudaMemsetAsync(out_sum, 0, sizeof(float), (cudaStream_t)stream);
+    cudaMemsetAsync(tie_count, 0, sizeof(int), (cudaStream_t)stream);
+    const int per_block = kMinResolveThreads * kMinResolvePix;
+    dim3 grid((unsigned)((n_total + per_block - 1) / per_block)), block(kMinResolveThreads);
+    TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(min_resolve_kernel<F>, grid, block, 0, stream, L, n_groups, n_total, band, out_sum, tie_count));
+    return check_launch("tcsfm_pair_min_resolve");
 }

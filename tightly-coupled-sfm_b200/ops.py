@@ -309,8 +309,8 @@ class FrameLossFn(torch.autograd.Function):
             min_sum = None
             if fwd_idx and (flags & _cabi.ARITH_FAST) and len(fwd_idx) > 1:
                 # tolerance-level diff values: the near-ties of the per-pixel min are re-decided with the exact arithmetic
-                min_sum, tie_list, tie_count = _raw.min_reduce_ties(lib(), diff[fwd_idx[0]], step * n_px, len(fwd_idx), n_px)
-                _raw.pair_tie_resolve(lib(), batch, fwd_idx, meta["w_l1"], meta["w_ssim"], flags, tie_list, tie_count)
+                # (one launch: per-pixel min, its near-ties kept in shared memory and re-evaluated right away)
+                min_sum, tie_count = _raw.pair_min_resolve(lib(), batch, fwd_idx, meta["w_l1"], meta["w_ssim"], flags)
                 global LAST_TIE_COUNT
                 LAST_TIE_COUNT = tie_count
             elif fwd_idx:
