@@ -822,3 +822,39 @@ def test_graphed_train_step_matches_eager():
     # up to 2 lr, so the parameters are compared in the mean)
     for p, q in zip(step_a.parameters(), step_b.parameters()):
         assert float((p - q).abs().mean()) < 2e-5, float((p - q).abs().mean())
+
+
+def test_min_resolve_one_launch_equals_the_two_launch_form():
+    """tcsfm_pair_min_resolve (per-pixel min + exact re-evaluation of its near-ties, ties kept in shared memory) against
+    tcsfm_min_reduce_ties + tcsfm_pair_tie_resolve at config 2: same patched diff maps, same tie count, same sum; the
+    patched values are the exact kernels' and the arg-min over the sources is the exact arithmetic's everywhere."""
+    from tcsfm_b200 import _raw
+    L = _lib.lib()
+    fr = frames(8, 192, 640, 0.01, synth.KITTI_DEPTH_RANGE, seed=31)
+    flags = _cabi.SSIM | _cabi.AUTO_MASK | _cabi.DEPTH_MASK | _cabi.DEPTH_CONSIST
+
+    def forward(fl):
+        groups = []
+        for j in range(2):
+            kinv, proj = stn.projection_matrices(-fr["poses"][j], fr["K"])
+            groups.append({"tgt_img": fr["target"], "ref_img": fr["sources"][j], "tgt_depth": fr["depths"][0],
+                           "ref_depth": fr["depths"][1 + j], "kinv": kinv, "proj": proj})
+        batch = _raw.PairBatch(groups)
+        diff, _, _, _ = _raw.pair_loss_fwd(L, batch, 0.15, 0.85, fl)
+        return batch, diff
+
+    _, d_exact = forward(flags)
+    fast = flags | _cabi.ARITH_FAST
+    batch_a, d_a = forward(fast)
+    n_px = d_a[0].numel()
+    sum_a, tie_list, tie_count = _raw.min_reduce_ties(L, d_a[0], n_px, 2, n_px)
+    _raw.pair_tie_resolve(L, batch_a, [0, 1], 0.15, 0.85, fast, tie_list, tie_count)
+    batch_b, d_b = forward(fast)
+    sum_b, count_b = _raw.pair_min_resolve(L, batch_b, [0, 1], 0.15, 0.85, fast)
+    assert int(count_b) == int(tie_count) > 0
+    assert torch.equal(d_a, d_b)
+    assert abs(float(sum_a) - float(sum_b)) <= 1e-5 * abs(float(sum_a))
+    idx = tie_list[:int(tie_count)].long()
+    for j in range(2):
+        assert torch.equal(d_b[j].flatten()[idx], d_exact[j].flatten()[idx])
+    assert torch.equal(torch.min(d_b.reshape(2, -1), 0)[1], torch.min(d_exact.reshape(2, -1), 0)[1])
