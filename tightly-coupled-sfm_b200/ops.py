@@ -64,19 +64,6 @@ def _guard(t):
     return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
 
 
-_SIDE_STREAMS = {}
-
-
-def side_stream(dev):
-    """One auxiliary stream per device for the independent branches of a step (K^-1 next to disp -> depth, the pose
-    chain rule next to the depth -> disparity chain rule); fork / join are plain events, so CUDA graphs capture them
-    as parallel branches."""
-    side = _SIDE_STREAMS.get(dev)
-    if side is None:
-        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
-    return side
-
-
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -359,25 +346,11 @@ class FrameLossFn(torch.autograd.Function):
                 lib(), ctx.batch, mask, sums, coef, g_scalars, g_min, (min_first, stride, min_pos, len(fwd_idx)),
                 g_depths, [grp[3] for grp in groups], [grp[4] for grp in groups],
                 meta["w_l1"], meta["w_ssim"], ctx.flags, need_ref)
-            # the two chain rules behind the pair kernel are independent: pose on a side stream, disparity on this one
-            joined = None
-            if K.is_cuda:
-                main, side = torch.cuda.current_stream(K.device), side_stream(K.device)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    g_pose = _raw.pose_proj_bwd(lib(), poses, K, -1.0, g_proj.reshape(-1, 3, 4))
-                    joined = torch.cuda.Event()
-                    joined.record(side)
-                g_proj.record_stream(side)
-                g_pose.record_stream(main)
-            else:
-                g_pose = _raw.pose_proj_bwd(lib(), poses, K, -1.0, g_proj.reshape(-1, 3, 4))
+            g_pose = _raw.pose_proj_bwd(lib(), poses, K, -1.0, g_proj.reshape(-1, 3, 4))
             g_disps = []
             for i in range(0, len(depths), 4):
                 g_disps += _raw.disp_to_depth_bwd(lib(), [g_depths[j] for j in range(i, min(i + 4, len(depths)))],
                                                   depths[i:i + 4], ctx.disp_range, disp_hw=ctx.disp_hw)
-            if joined is not None:
-                torch.cuda.current_stream(K.device).wait_event(joined)
         g_poses = tuple(g_pose[i * b:(i + 1) * b] for i in range(g))
         return (None, None, None) + g_poses + (None,) * meta["n_img"] + tuple(g_disps)
 

@@ -85,6 +85,9 @@ def inverse_intrinsics(intrinsics):
     return torch.linalg.inv_ex(intrinsics.detach())[0]
 
 
+_SIDE_STREAMS = {}
+
+
 def inverse_intrinsics_forked(intrinsics):
     """K^-1 as above, computed on a side stream so that the handful of tiny batched-LU launches overlap the
     launches that do not need it (disp -> depth, pose -> K[R|t]).  Returns (kinv, event): the consumer's
@@ -94,7 +97,9 @@ def inverse_intrinsics_forked(intrinsics):
         return inverse_intrinsics(intrinsics), None
     dev = intrinsics.device
     main = torch.cuda.current_stream(dev)
-    side = ops.side_stream(dev)
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
     side.wait_stream(main)
     with torch.cuda.stream(side):
         kinv = inverse_intrinsics(intrinsics).contiguous()     # (torch.inverse returns K^-1 column-major)
