@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 12
+#define TCSFM_ABI_VERSION 13
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -211,6 +211,11 @@ int tcsfm_smooth_bwd(const float* disp, const float* img, int64_t img_sb, int64_
  *      (utils/custom_transforms.py:74: torch.from_numpy(im).float() / 255) and ships fp32 to the GPU.  dst[i] =
  *      float(src[i]) / 255 with the same IEEE division, so frames can cross the host link as bytes. */
 int tcsfm_u8_to_float(const unsigned char* src, float* dst, int64_t n, void* stream);
+
+/* K^-1 of B row-major 3x3 fp32 matrices -> row-major [B,9], with the bits of `intrinsics.inverse()` on CUDA
+ * (models/stn.py:257: cuBLAS batched LU + triangular solves, ten launches) in one launch; the arithmetic ordering was
+ * matched bit for bit on probed inverses (tools/probe_kinv.py, tools/match_kinv.py). */
+int tcsfm_intrinsics_inverse(const float* K, float* kinv, int B, void* stream);
 
 /* ---- glue of Compute_Loss.forward (losses.py:75-140) ----------------------------
  * pose [N,6] (times `sign`; every call site passes -pose) -> K @ [Rx Ry Rz | t] as [N,12]

@@ -265,3 +265,18 @@ def test_disp_upsample_to_depth_vs_interpolate(shapes):
         assert dep.shape == ref.shape and same(dep, ref)
         ref.backward(g)
         assert gd.shape == d.shape and rel_l2(gd, d.grad) < 1e-5
+
+
+def test_intrinsics_inverse_has_the_bits_of_torch_on_cuda():
+    """tcsfm_intrinsics_inverse against inverses that torch.linalg.inv_ex produced on a B200 (tests/golden/
+    kinv_cuda_probe.npz: the first 300 matrices of each family of tools/probe_kinv.py -- camera intrinsics, skewed,
+    lower-triangular, dense, badly scaled): bit for bit, signs of zeros included."""
+    import os
+    import numpy as np
+    from tcsfm_b200 import _raw
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "kinv_cuda_probe.npz"))
+    for fam in ("kitti", "skew", "dense", "general", "lower"):
+        k = torch.from_numpy(d[fam + "_in"])
+        want = torch.from_numpy(d[fam + "_inv"])
+        got = _raw.intrinsics_inverse(emu(), k)
+        assert torch.equal(got.view(torch.int32), want.view(torch.int32)), fam

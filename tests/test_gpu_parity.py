@@ -858,3 +858,30 @@ def test_min_resolve_one_launch_equals_the_two_launch_form():
     for j in range(2):
         assert torch.equal(d_b[j].flatten()[idx], d_exact[j].flatten()[idx])
     assert torch.equal(torch.min(d_b.reshape(2, -1), 0)[1], torch.min(d_exact.reshape(2, -1), 0)[1])
+
+
+def test_intrinsics_inverse_bit_exact_vs_torch_cuda():
+    """stn.inverse_intrinsics (one launch of the library's batched 3x3 LU) against torch.linalg.inv_ex and
+    torch.inverse on the same GPU, 50 000 matrices per family: bit for bit."""
+    g = torch.Generator().manual_seed(5)
+    n = 50000
+    fx = 200 + 1000 * torch.rand(n, generator=g)
+    kitti = torch.zeros(n, 3, 3)
+    kitti[:, 0, 0], kitti[:, 1, 1] = fx, fx * (0.9 + 0.2 * torch.rand(n, generator=g))
+    kitti[:, 0, 2], kitti[:, 1, 2], kitti[:, 2, 2] = 100 + 600 * torch.rand(n, generator=g), 50 + 300 * torch.rand(n, generator=g), 1.0
+    skew = kitti.clone()
+    skew[:, 0, 1] = 5 * torch.randn(n, generator=g)
+    fams = {"kitti": kitti, "skew": skew, "lower": kitti.transpose(1, 2).contiguous(),
+            "dense": torch.randn(n, 3, 3, generator=g) + 3 * torch.eye(3),
+            "scaled": torch.randn(n, 3, 3, generator=g) * torch.tensor([300.0, 30.0, 1.0]).view(1, 3, 1),
+            "perm": torch.randn(n, 3, 3, generator=g)[:, [2, 0, 1]]}
+    for name, k in fams.items():
+        k = k.to(DEV)
+        got = stn.inverse_intrinsics(k)
+        want = torch.linalg.inv_ex(k)[0]
+        assert got.is_contiguous() and got.shape == (n, 3, 3)
+        bad = (got.view(torch.int32) != want.contiguous().view(torch.int32)).flatten(1).any(1)
+        assert int(bad.sum()) == 0, (name, int(bad.sum()))
+        assert torch.equal(got[:256], torch.inverse(k[:256]))
+    one = stn.inverse_intrinsics(fams["kitti"][:1].to(DEV))                      # batch 1
+    assert torch.equal(one, torch.inverse(fams["kitti"][:1].to(DEV)))

@@ -168,6 +168,18 @@ def ssim_mean_bwd(lib, x, y, g_mean, need_x=True, need_y=True, flags=0):
     return g_x, g_y
 
 
+def intrinsics_inverse(lib, K):
+    """K^-1 [B,3,3] (row-major, contiguous) of fp32 matrices [B,3,3] with the bits of K.inverse() on CUDA, one launch."""
+    _expect(K, (K.shape[0], 3, 3), "intrinsics")
+    K = _f32c(K, "intrinsics")
+    out = torch.empty_like(K)
+    with _timing.launch("intrinsics_inverse", K.is_cuda):
+        rc = lib.tcsfm_intrinsics_inverse(_ptr(K), _ptr(out), K.shape[0], _stream(K))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return out
+
+
 def u8_to_float(lib, src, out=None):
     """float(src) / 255 (the loader's conversion, utils/custom_transforms.py:74) of a uint8 tensor; `out`: optional
     preallocated fp32 tensor of the same shape (e.g. the static input buffer of a CUDA graph)."""

@@ -122,6 +122,63 @@ __global__ void pose_proj_bwd_kernel(const float* __restrict__ pose, float sign,
     out[3] = sign * g_rx; out[4] = sign * g_ry; out[5] = sign * g_rz;
 }
 
+// K^-1 of [B,3,3] fp32 matrices with the bits of torch.inverse / torch.linalg.inv_ex on CUDA (models/stn.py:257), which
+// run cuBLAS' batched LU (getrf) and two triangular solves on the permuted identity (getrs): ten small launches.  The
+// ordering of that arithmetic was identified by matching 20 000 probed inverses bit for bit (tools/probe_kinv.py,
+// tools/match_kinv.py; camera intrinsics, skewed, lower-triangular and dense matrices, signs of zeros included):
+//   getrf: partial pivoting on the first maximal |a| of the column; multipliers l = a * RN(1 / pivot); Schur update
+//          a_ij = fma(-l_i, u_j, a_ij);
+//   getrs: forward substitution y_i = fma(-l_ik, y_k, y_i); backward substitution column by column from the last
+//          (x_2 first, then b_0 takes u_02 x_2 before u_01 x_1), fma updates, IEEE division by the diagonal.
+// One thread per matrix; the output is row-major [B,9], which is what the warp kernels read.
+__global__ void intrinsics_inverse_kernel(const float* __restrict__ K, float* __restrict__ kinv, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float a[3][3];
+    int perm[3] = {0, 1, 2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a[i][j] = __ldg(K + b * 9 + i * 3 + j);
+#pragma unroll
+    for (int col = 0; col < 2; ++col) {
+        int piv = col;
+#pragma unroll
+        for (int i = col + 1; i < 3; ++i)
+            if (fabsf(a[i][col]) > fabsf(a[piv][col])) piv = i;
+#pragma unroll
+        for (int i = col + 1; i < 3; ++i)
+            if (piv == i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { const float t = a[col][j]; a[col][j] = a[i][j]; a[i][j] = t; }
+                const int t = perm[col]; perm[col] = perm[i]; perm[i] = t;
+            }
+        const float r = __frcp_rn(a[col][col]);
+#pragma unroll
+        for (int i = col + 1; i < 3; ++i) {
+            a[i][col] = __fmul_rn(a[i][col], r);
+#pragma unroll
+            for (int j = col + 1; j < 3; ++j) a[i][j] = __fmaf_rn(-a[i][col], a[col][j], a[i][j]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {                       // column c of the inverse: solve L U x = P e_c
+        float y0 = perm[0] == c ? 1.f : 0.f, y1 = perm[1] == c ? 1.f : 0.f, y2 = perm[2] == c ? 1.f : 0.f;
+        y1 = __fmaf_rn(-a[1][0], y0, y1);
+        y2 = __fmaf_rn(-a[2][0], y0, y2);
+        y2 = __fmaf_rn(-a[2][1], y1, y2);
+        const float x2 = __fdiv_rn(y2, a[2][2]);
+        y1 = __fmaf_rn(-a[1][2], x2, y1);
+        y0 = __fmaf_rn(-a[0][2], x2, y0);
+        const float x1 = __fdiv_rn(y1, a[1][1]);
+        y0 = __fmaf_rn(-a[0][1], x1, y0);
+        const float x0 = __fdiv_rn(y0, a[0][0]);
+        kinv[b * 9 + 0 * 3 + c] = x0;
+        kinv[b * 9 + 1 * 3 + c] = x1;
+        kinv[b * 9 + 2 * 3 + c] = x2;
+    }
+}
+
 // disp_to_depth (utils/learning_helpers.py:77-86) for up to 4 equally sized maps in one launch:
 // depth = 1 / (min_disp + (max_disp - min_disp) * disp), each step rounded like the eager operators
 // (mul by scalar, add scalar, reciprocal).  Backward: g_disp = -g_depth * depth^2 * (max_disp - min_disp).
@@ -357,6 +414,12 @@ __global__ void frame_bwd_prepare_kernel(const float* __restrict__ g_out, const 
 }  // namespace tcsfm
 
 using namespace tcsfm;
+
+extern "C" int tcsfm_intrinsics_inverse(const float* K, float* kinv, int B, void* stream) {
+    if (!K || !kinv || B <= 0) { set_error("tcsfm_intrinsics_inverse: bad arguments"); return 1; }
+    TCSFM_LAUNCH(intrinsics_inverse_kernel, dim3((B + 63) / 64), dim3(64), 0, stream, K, kinv, B);
+    return check_launch("tcsfm_intrinsics_inverse");
+}
 
 extern "C" int tcsfm_u8_to_float(const unsigned char* src, float* dst, int64_t n, void* stream) {
     if (!src || !dst || n <= 0) { set_error("tcsfm_u8_to_float: bad arguments"); return 1; }

@@ -77,36 +77,24 @@ def pose_vec2mat(vec, rotation_mode='euler'):
 
 
 def inverse_intrinsics(intrinsics):
-    """`intrinsics.inverse()` (models/stn.py:257) with the reference's bits (the same batched LU),
-    recomputed on every call like the reference does.  `inv_ex` skips the device -> host error
-    check of `.inverse()`, so the call neither synchronises nor breaks CUDA-graph capture; callers
-    that warp several times with one K (Compute_Loss.forward, solve_pose_iteratively) compute it
-    once per call and pass it down."""
-    return torch.linalg.inv_ex(intrinsics.detach())[0]
-
-
-_SIDE_STREAMS = {}
+    """`intrinsics.inverse()` (models/stn.py:257), recomputed on every call like the reference does.  On CUDA fp32
+    tensors it is ONE launch of the library's own batched 3x3 LU, which reproduces the bits of torch's cuBLAS path
+    (getrf + getrs on the identity: ten launches and a layout copy) -- the ordering of that arithmetic was matched bit
+    for bit on probed inverses, see csrc/frame_kernels.cu.  It neither synchronises nor breaks CUDA-graph capture.
+    Other tensors go through `torch.linalg.inv_ex` (no device -> host error check either)."""
+    k = intrinsics.detach()
+    if k.is_cuda and k.dtype == torch.float32 and k.dim() == 3:
+        from . import _raw
+        with ops._guard(k):
+            return _raw.intrinsics_inverse(ops.lib(), k)
+    return torch.linalg.inv_ex(k)[0]
 
 
 def inverse_intrinsics_forked(intrinsics):
-    """K^-1 as above, computed on a side stream so that the handful of tiny batched-LU launches overlap the
-    launches that do not need it (disp -> depth, pose -> K[R|t]).  Returns (kinv, event): the consumer's
-    stream waits for `event` (None on the CPU) before the first kernel that reads kinv.  The fork / join is
-    plain event traffic, so it is captured into CUDA graphs as a parallel branch."""
-    if not intrinsics.is_cuda:
-        return inverse_intrinsics(intrinsics), None
-    dev = intrinsics.device
-    main = torch.cuda.current_stream(dev)
-    side = _SIDE_STREAMS.get(dev)
-    if side is None:
-        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        kinv = inverse_intrinsics(intrinsics).contiguous()     # (torch.inverse returns K^-1 column-major)
-        event = torch.cuda.Event()
-        event.record(side)
-    kinv.record_stream(main)
-    return kinv, event
+    """(K^-1, event): kept for callers that overlapped torch's ten-launch inverse with other work on a side stream.  The
+    single-launch inverse above costs less than the fork / join did, so it now runs on the caller's stream and the
+    event is always None."""
+    return inverse_intrinsics(intrinsics).contiguous(), None
 
 
 def projection_matrices(pose, intrinsics, kinv=None):
