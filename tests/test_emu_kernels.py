@@ -268,13 +268,13 @@ def test_disp_upsample_to_depth_vs_interpolate(shapes):
 
 
 def test_intrinsics_inverse_has_the_bits_of_torch_on_cuda():
-    """tcsfm_intrinsics_inverse against inverses that torch.linalg.inv_ex produced on a B200 (tests/golden/
+    """tcsfm_intrinsics_inverse against inverses that torch.linalg.inv_ex produced on a B200 (tests/golden/probes/
     kinv_cuda_probe.npz: the first 300 matrices of each family of tools/probe_kinv.py -- camera intrinsics, skewed,
     lower-triangular, dense, badly scaled): bit for bit, signs of zeros included."""
     import os
     import numpy as np
     from tcsfm_b200 import _raw
-    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "kinv_cuda_probe.npz"))
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "probes", "kinv_cuda_probe.npz"))
     for fam in ("kitti", "skew", "dense", "general", "lower"):
         k = torch.from_numpy(d[fam + "_in"])
         want = torch.from_numpy(d[fam + "_inv"])
