@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 13
+#define TCSFM_ABI_VERSION 14
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -216,6 +216,17 @@ int tcsfm_u8_to_float(const unsigned char* src, float* dst, int64_t n, void* str
  * (models/stn.py:257: cuBLAS batched LU + triangular solves, ten launches) in one launch; the arithmetic ordering was
  * matched bit for bit on probed inverses (tools/probe_kinv.py, tools/match_kinv.py). */
 int tcsfm_intrinsics_inverse(const float* K, float* kinv, int B, void* stream);
+
+/* The glue on either side of the pair kernels of one frame (Compute_Loss.forward, losses.py:86-122) as one launch each:
+ * prologue = tcsfm_disp_to_depth_fwd of `count` (<= 4) maps of n elements + tcsfm_pose_proj_fwd of n_groups (<= 8) pose
+ * tensors [B, >= 6] read in place through a pointer table (row stride `pose_stride` floats; proj [n_groups*B,3,4]);
+ * epilogue = the two chain rules (g_pose [n_groups*B,6]). */
+int tcsfm_frame_prologue(const float* const* disp, float* const* depth, int count, int64_t n, float min_disp, float range,
+                         const float* const* pose, int n_groups, int pose_stride, float sign, const float* K, int B,
+                         float* proj, int flags, void* stream);
+int tcsfm_frame_epilogue(const float* const* g_depth, const float* const* depth, float* const* g_disp, int count, int64_t n,
+                         float range, const float* const* pose, int n_groups, int pose_stride, float sign,
+                         const float* K, int B, const float* g_proj, float* g_pose, void* stream);
 
 /* ---- glue of Compute_Loss.forward (losses.py:75-140) ----------------------------
  * pose [N,6] (times `sign`; every call site passes -pose) -> K @ [Rx Ry Rz | t] as [N,12]

@@ -517,6 +517,54 @@ def disp_to_depth_bwd(lib, g_depths, depths, disp_range, disp_hw=None):
     return g_disps
 
 
+def pose_rows(poses):
+    """The pose tensors of a frame's groups as (list of fp32 tensors readable in place, row stride in floats), or None
+    when they do not share a layout (the caller then concatenates them)."""
+    if not poses or len(poses) > 8:
+        return None
+    stride = poses[0].stride(0)
+    for p in poses:
+        if p.dtype != torch.float32 or p.dim() != 2 or p.shape[1] < 6 or p.stride(1) != 1 or p.stride(0) != stride \
+                or p.shape[0] != poses[0].shape[0] or stride < 6:
+            return None
+    return list(poses), stride
+
+
+def frame_prologue(lib, disps, min_disp, disp_range, poses, pose_stride, K, sign, flags):
+    """disp -> depth of <= 4 equally shaped maps and pose -> K[R|t] of the groups' pose tensors as ONE launch.
+    Returns (depths, proj [G*B,3,4])."""
+    disps = [_f32c(d, "disp") for d in disps]
+    if any(d.shape != disps[0].shape for d in disps):
+        raise ValueError("frame_prologue: the maps of one launch must share a shape")
+    K = _f32c(K, "K")
+    b = K.shape[0]
+    _expect(K, (b, 3, 3), "K")
+    depths = [torch.empty_like(d) for d in disps]
+    proj = torch.empty((len(poses) * b, 3, 4), dtype=torch.float32, device=K.device)
+    with _timing.launch("frame_prologue", K.is_cuda):
+        rc = lib.tcsfm_frame_prologue(_ptr_table(disps), _ptr_table(depths), len(disps), disps[0].numel(), min_disp, disp_range,
+                                      _ptr_table(poses), len(poses), pose_stride, sign, _ptr(K), b, _ptr(proj), flags, _stream(K))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return depths, proj
+
+
+def frame_epilogue(lib, g_depths, depths, disp_range, poses, pose_stride, K, sign, g_proj):
+    """The chain rules of frame_prologue as ONE launch: (g_disps, g_pose [G*B,6])."""
+    g_depths = [_f32c(g, "g_depth") for g in g_depths]
+    K, g_proj = _f32c(K, "K"), _f32c(g_proj, "g_proj")
+    b = K.shape[0]
+    g_disps = [torch.empty_like(d) for d in depths]
+    g_pose = torch.empty((len(poses) * b, 6), dtype=torch.float32, device=K.device)
+    with _timing.launch("frame_epilogue", K.is_cuda):
+        rc = lib.tcsfm_frame_epilogue(_ptr_table(g_depths), _ptr_table(depths), _ptr_table(g_disps), len(depths), depths[0].numel(),
+                                      disp_range, _ptr_table(poses), len(poses), pose_stride, sign, _ptr(K), b, _ptr(g_proj),
+                                      _ptr(g_pose), _stream(K))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return g_disps, g_pose
+
+
 def smooth_fwd(lib, disp, img):
     disp = _f32c(disp, "disp")
     img, sb, sc = image_view(img, "img")

@@ -46,14 +46,13 @@ __device__ __forceinline__ Euler euler_matrices(float rx, float ry, float rz) {
     return e;
 }
 
+// pose row `p6` (6 floats) of item i -> proj[i] = K[i % Bk] @ [R | t]
 template <bool kNoFma>
-__global__ void pose_proj_fwd_kernel(const float* __restrict__ pose, float sign, const float* __restrict__ K, int Bk,
-                                     float* __restrict__ proj, int N) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+__device__ __forceinline__ void pose_proj_fwd_body(const float* __restrict__ p6, float sign, const float* __restrict__ K, int Bk,
+                                                   float* __restrict__ proj, int i) {
     float p[6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) p[j] = sign * pose[i * 6 + j];
+    for (int j = 0; j < 6; ++j) p[j] = sign * p6[j];
     const Euler e = euler_matrices(p[3], p[4], p[5]);
     float XY[9], R[9], T[12], P[12], Km[9];
     matmul3<3, kNoFma>(e.X, e.Y, XY);
@@ -70,13 +69,18 @@ __global__ void pose_proj_fwd_kernel(const float* __restrict__ pose, float sign,
     for (int j = 0; j < 12; ++j) proj[i * 12 + j] = P[j];
 }
 
-__global__ void pose_proj_bwd_kernel(const float* __restrict__ pose, float sign, const float* __restrict__ K, int Bk,
-                                     const float* __restrict__ g_proj, float* __restrict__ g_pose, int N) {
+template <bool kNoFma>
+__global__ void pose_proj_fwd_kernel(const float* __restrict__ pose, float sign, const float* __restrict__ K, int Bk,
+                                     float* __restrict__ proj, int N) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i < N) pose_proj_fwd_body<kNoFma>(pose + i * 6, sign, K, Bk, proj, i);
+}
+
+__device__ __forceinline__ void pose_proj_bwd_body(const float* __restrict__ p6, float sign, const float* __restrict__ K, int Bk,
+                                                   const float* __restrict__ g_proj, float* __restrict__ g_pose, int i) {
     float p[6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) p[j] = sign * pose[i * 6 + j];
+    for (int j = 0; j < 6; ++j) p[j] = sign * p6[j];
     const Euler e = euler_matrices(p[3], p[4], p[5]);
     const float* Km = K + (i % Bk) * 9;
     const float* gP = g_proj + i * 12;
@@ -120,6 +124,12 @@ __global__ void pose_proj_bwd_kernel(const float* __restrict__ pose, float sign,
     float* out = g_pose + i * 6;
     out[0] = sign * gT[3]; out[1] = sign * gT[7]; out[2] = sign * gT[11];
     out[3] = sign * g_rx; out[4] = sign * g_ry; out[5] = sign * g_rz;
+}
+
+__global__ void pose_proj_bwd_kernel(const float* __restrict__ pose, float sign, const float* __restrict__ K, int Bk,
+                                     const float* __restrict__ g_proj, float* __restrict__ g_pose, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) pose_proj_bwd_body(pose + i * 6, sign, K, Bk, g_proj, g_pose, i);
 }
 
 // K^-1 of [B,3,3] fp32 matrices with the bits of torch.inverse / torch.linalg.inv_ex on CUDA (models/stn.py:257), which
@@ -187,9 +197,8 @@ struct MapPtrs { const float* in[4]; const float* aux[4]; float* out[4]; int cou
 // kVec = 4: 16-byte accesses (n % 4 == 0 and every pointer 16-byte aligned, checked by the launcher); the loads of all
 // maps of a thread are in flight before the first store.
 template <int kVec>
-__global__ void __launch_bounds__(256)
-disp_to_depth_fwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float min_disp, float range) {
-    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kVec;
+__device__ __forceinline__ void disp_to_depth_fwd_body(const MapPtrs& M, int64_t n, float min_disp, float range, int block) {
+    const int64_t i = ((int64_t)block * 256 + threadIdx.x) * kVec;
     if (i >= n) return;
     float v[4][kVec];
 #pragma unroll
@@ -214,8 +223,13 @@ disp_to_depth_fwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float min
 
 template <int kVec>
 __global__ void __launch_bounds__(256)
-disp_to_depth_bwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float range) {
-    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kVec;
+disp_to_depth_fwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float min_disp, float range) {
+    disp_to_depth_fwd_body<kVec>(M, n, min_disp, range, blockIdx.x);
+}
+
+template <int kVec>
+__device__ __forceinline__ void disp_to_depth_bwd_body(const MapPtrs& M, int64_t n, float range, int block) {
+    const int64_t i = ((int64_t)block * 256 + threadIdx.x) * kVec;
     if (i >= n) return;
     float g[4][kVec], d[4][kVec];
 #pragma unroll
@@ -239,6 +253,42 @@ disp_to_depth_bwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float ran
             if (kVec == 4) *reinterpret_cast<float4*>(M.out[k] + i) = make_float4(g[k][0], g[k][1 % kVec], g[k][2 % kVec], g[k][3 % kVec]);
             else M.out[k][i] = g[k][0];
         }
+}
+
+template <int kVec>
+__global__ void __launch_bounds__(256)
+disp_to_depth_bwd_kernel(const __grid_constant__ MapPtrs M, int64_t n, float range) {
+    disp_to_depth_bwd_body<kVec>(M, n, range, blockIdx.x);
+}
+
+// The glue on either side of the pair kernels as ONE launch each (a small kernel costs ~3 us of a 0.3 ms step whatever
+// it does): prologue = disp -> depth of up to four maps + pose -> K[R|t] of every group, the poses read through a
+// pointer table so that no concatenated copy is needed; epilogue = their two chain rules.  Blocks [0, nb_maps) work
+// on the maps, the blocks behind them on the poses (item i = group i / per, row i % per).
+struct FrameGlue {
+    MapPtrs M;
+    int64_t n;
+    float min_disp, range, sign;
+    int nb_maps, pose_stride, per, N, Bk;
+    const float* pose[8];
+    const float* K;
+    float* proj;
+    const float* g_proj;
+    float* g_pose;
+};
+
+template <int kVec, bool kNoFma>
+__global__ void __launch_bounds__(256) frame_prologue_kernel(const __grid_constant__ FrameGlue G) {
+    if ((int)blockIdx.x < G.nb_maps) { disp_to_depth_fwd_body<kVec>(G.M, G.n, G.min_disp, G.range, blockIdx.x); return; }
+    const int i = ((int)blockIdx.x - G.nb_maps) * 256 + threadIdx.x;
+    if (i < G.N) pose_proj_fwd_body<kNoFma>(G.pose[i / G.per] + (i % G.per) * G.pose_stride, G.sign, G.K, G.Bk, G.proj, i);
+}
+
+template <int kVec>
+__global__ void __launch_bounds__(256) frame_epilogue_kernel(const __grid_constant__ FrameGlue G) {
+    if ((int)blockIdx.x < G.nb_maps) { disp_to_depth_bwd_body<kVec>(G.M, G.n, G.range, blockIdx.x); return; }
+    const int i = ((int)blockIdx.x - G.nb_maps) * 256 + threadIdx.x;
+    if (i < G.N) pose_proj_bwd_body(G.pose[i / G.per] + (i % G.per) * G.pose_stride, G.sign, G.K, G.Bk, G.g_proj, G.g_pose, i);
 }
 
 static bool maps_vectorisable(const MapPtrs& M, int64_t n) {
@@ -545,4 +595,57 @@ extern "C" int tcsfm_frame_bwd_prepare(const float* g_out, const float* g_total,
     if ((!g_out && !g_total) || !cfg || !g_scalars || !g_min || cfg->n_groups <= 0 || cfg->n_groups > 8) { set_error("tcsfm_frame_bwd_prepare: bad arguments"); return 1; }
     TCSFM_LAUNCH(frame_bwd_prepare_kernel, dim3(1), dim3(32), 0, stream, g_out, g_total, *cfg, g_scalars, g_min);
     return check_launch("tcsfm_frame_bwd_prepare");
+}
+
+
+static int fill_glue(FrameGlue& G, int count, int64_t n, const float* const* pose, int n_groups, int pose_stride, float sign,
+                     const float* K, int B, const char* who) {
+    if (count < 1 || count > 4 || n <= 0 || !pose || n_groups < 1 || n_groups > 8 || pose_stride < 6 || !K || B <= 0) {
+        set_error("%s: bad arguments", who); return 1;
+    }
+    G.M.count = count;
+    G.n = n;
+    G.sign = sign;
+    G.pose_stride = pose_stride; G.per = B; G.N = n_groups * B; G.Bk = B;
+    for (int g = 0; g < n_groups; ++g) {
+        if (!pose[g]) { set_error("%s: null pose pointer", who); return 1; }
+        G.pose[g] = pose[g];
+    }
+    G.K = K;
+    return 0;
+}
+
+extern "C" int tcsfm_frame_prologue(const float* const* disp, float* const* depth, int count, int64_t n, float min_disp, float range,
+                                    const float* const* pose, int n_groups, int pose_stride, float sign, const float* K, int B,
+                                    float* proj, int flags, void* stream) {
+    FrameGlue G;
+    memset(&G, 0, sizeof(G));
+    if (!disp || !depth || !proj) { set_error("tcsfm_frame_prologue: null pointer"); return 1; }
+    if (int rc = fill_glue(G, count, n, pose, n_groups, pose_stride, sign, K, B, "tcsfm_frame_prologue")) return rc;
+    for (int k = 0; k < count; ++k) { G.M.in[k] = disp[k]; G.M.out[k] = depth[k]; }
+    G.min_disp = min_disp; G.range = range; G.proj = proj;
+    const bool vec = maps_vectorisable(G.M, n);
+    G.nb_maps = (int)(((vec ? n / 4 : n) + 255) / 256);
+    dim3 grid(G.nb_maps + (G.N + 255) / 256), block(256);
+    const bool nofma = (flags & TCSFM_ARITH_BMM_NOFMA) != 0;
+    if (vec) { if (nofma) TCSFM_LAUNCH((frame_prologue_kernel<4, true>), grid, block, 0, stream, G); else TCSFM_LAUNCH((frame_prologue_kernel<4, false>), grid, block, 0, stream, G); }
+    else { if (nofma) TCSFM_LAUNCH((frame_prologue_kernel<1, true>), grid, block, 0, stream, G); else TCSFM_LAUNCH((frame_prologue_kernel<1, false>), grid, block, 0, stream, G); }
+    return check_launch("tcsfm_frame_prologue");
+}
+
+extern "C" int tcsfm_frame_epilogue(const float* const* g_depth, const float* const* depth, float* const* g_disp, int count, int64_t n,
+                                    float range, const float* const* pose, int n_groups, int pose_stride, float sign,
+                                    const float* K, int B, const float* g_proj, float* g_pose, void* stream) {
+    FrameGlue G;
+    memset(&G, 0, sizeof(G));
+    if (!g_depth || !depth || !g_disp || !g_proj || !g_pose) { set_error("tcsfm_frame_epilogue: null pointer"); return 1; }
+    if (int rc = fill_glue(G, count, n, pose, n_groups, pose_stride, sign, K, B, "tcsfm_frame_epilogue")) return rc;
+    for (int k = 0; k < count; ++k) { G.M.in[k] = g_depth[k]; G.M.aux[k] = depth[k]; G.M.out[k] = g_disp[k]; }
+    G.range = range; G.g_proj = g_proj; G.g_pose = g_pose;
+    const bool vec = maps_vectorisable(G.M, n);
+    G.nb_maps = (int)(((vec ? n / 4 : n) + 255) / 256);
+    dim3 grid(G.nb_maps + (G.N + 255) / 256), block(256);
+    if (vec) TCSFM_LAUNCH(frame_epilogue_kernel<4>, grid, block, 0, stream, G);
+    else TCSFM_LAUNCH(frame_epilogue_kernel<1>, grid, block, 0, stream, G);
+    return check_launch("tcsfm_frame_epilogue");
 }

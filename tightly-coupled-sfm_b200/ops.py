@@ -289,11 +289,20 @@ class FrameLossFn(torch.autograd.Function):
             # disparities of a lower pyramid scale arrive at their own resolution: the nearest upsample of
             # losses.py:86-87,102-103 happens inside the disp -> depth kernel
             full_hw = tuple(images[0].shape[-2:])
-            depths = []
-            for i in range(0, len(disps), 4):
-                depths += _raw.disp_to_depth_fwd(lib(), disps[i:i + 4], min_disp, max_disp - min_disp, out_hw=full_hw)
-            poses = torch.cat([p[:, 0:6] for p in poses_in], 0)
-            proj = _raw.pose_proj_fwd(lib(), poses, K, -1.0, pose_flags(b))
+            rows = _raw.pose_rows(poses_in)
+            glued = (rows is not None and len(disps) <= 4 and tuple(disps[0].shape[-2:]) == full_hw
+                     and all(d.shape == disps[0].shape for d in disps))
+            if glued:
+                # full-resolution disparities, poses readable in place: disp -> depth and pose -> K[R|t] in one launch
+                poses, pose_stride = rows
+                depths, proj = _raw.frame_prologue(lib(), disps, min_disp, max_disp - min_disp, poses, pose_stride, K, -1.0,
+                                                   pose_flags(b))
+            else:
+                depths = []
+                for i in range(0, len(disps), 4):
+                    depths += _raw.disp_to_depth_fwd(lib(), disps[i:i + 4], min_disp, max_disp - min_disp, out_hw=full_hw)
+                poses, pose_stride = [torch.cat([p[:, 0:6] for p in poses_in], 0)], 6
+                proj = _raw.pose_proj_fwd(lib(), poses[0], K, -1.0, pose_flags(b))
             specs = [{"tgt_img": images[ti], "ref_img": images[ri], "tgt_depth": depths[td], "ref_depth": depths[rd],
                       "kinv": kinv, "proj": proj[i * b:(i + 1) * b]} for i, (_, ti, ri, td, rd) in enumerate(groups)]
             batch = _raw.PairBatch(specs)
@@ -319,7 +328,8 @@ class FrameLossFn(torch.autograd.Function):
             # two separate tensors (not views of one buffer): callers may add to `total` in place
             terms, total = _raw.frame_finalize(lib(), sums, min_sum, cfg)
         if want_grad:
-            ctx.save_for_backward(mask, sums, coef, diff, poses, K, *depths)
+            ctx.save_for_backward(mask, sums, coef, diff, K, *depths, *poses)
+            ctx.n_depths, ctx.glued, ctx.pose_stride = len(depths), glued, pose_stride
             ctx.batch, ctx.cfg, ctx.meta, ctx.flags = batch, cfg, meta, flags
             ctx.min_info = (fwd_idx, step * n_px)
             ctx.disp_range = max_disp - min_disp
@@ -330,9 +340,10 @@ class FrameLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_terms, g_total):
         if g_terms is None and g_total is None:
-            return (None,) * (3 + len(ctx.meta["groups"]) + ctx.meta["n_img"] + len(ctx.saved_tensors) - 6)
-        mask, sums, coef, diff, poses, K = ctx.saved_tensors[:6]
-        depths = list(ctx.saved_tensors[6:])
+            return (None,) * (3 + len(ctx.meta["groups"]) + ctx.meta["n_img"] + ctx.n_depths)
+        mask, sums, coef, diff, K = ctx.saved_tensors[:5]
+        depths = list(ctx.saved_tensors[5:5 + ctx.n_depths])
+        poses = list(ctx.saved_tensors[5 + ctx.n_depths:])
         meta, groups = ctx.meta, ctx.meta["groups"]
         g, b = len(groups), K.shape[0]
         fwd_idx, stride = ctx.min_info
@@ -346,11 +357,15 @@ class FrameLossFn(torch.autograd.Function):
                 lib(), ctx.batch, mask, sums, coef, g_scalars, g_min, (min_first, stride, min_pos, len(fwd_idx)),
                 g_depths, [grp[3] for grp in groups], [grp[4] for grp in groups],
                 meta["w_l1"], meta["w_ssim"], ctx.flags, need_ref)
-            g_pose = _raw.pose_proj_bwd(lib(), poses, K, -1.0, g_proj.reshape(-1, 3, 4))
-            g_disps = []
-            for i in range(0, len(depths), 4):
-                g_disps += _raw.disp_to_depth_bwd(lib(), [g_depths[j] for j in range(i, min(i + 4, len(depths)))],
-                                                  depths[i:i + 4], ctx.disp_range, disp_hw=ctx.disp_hw)
+            if ctx.glued:                       # the two chain rules behind the pair kernel in one launch
+                g_disps, g_pose = _raw.frame_epilogue(lib(), [g_depths[j] for j in range(len(depths))], depths, ctx.disp_range,
+                                                      poses, ctx.pose_stride, K, -1.0, g_proj.reshape(-1, 3, 4))
+            else:
+                g_pose = _raw.pose_proj_bwd(lib(), poses[0], K, -1.0, g_proj.reshape(-1, 3, 4))
+                g_disps = []
+                for i in range(0, len(depths), 4):
+                    g_disps += _raw.disp_to_depth_bwd(lib(), [g_depths[j] for j in range(i, min(i + 4, len(depths)))],
+                                                      depths[i:i + 4], ctx.disp_range, disp_hw=ctx.disp_hw)
         g_poses = tuple(g_pose[i * b:(i + 1) * b] for i in range(g))
         return (None, None, None) + g_poses + (None,) * meta["n_img"] + tuple(g_disps)
 
