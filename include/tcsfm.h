@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 14
+#define TCSFM_ABI_VERSION 15
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -256,8 +256,20 @@ int tcsfm_disp_upsample_to_depth_fwd(const float* const* disp, float* const* dep
 int tcsfm_disp_upsample_to_depth_bwd(const float* const* g_depth, const float* const* depth, float* const* g_disp,
                                      int count, int B, int h, int w, int H, int W, float range, void* stream);
 
+typedef struct tcsfm_frame_cfg {
+    int32_t n_groups;       /* pair groups of the launch, in the reference's evaluation order      */
+    int32_t role[8];        /* 0 = inverse reconstruction (scalar, x w_inverse), 1 = forward (min)  */
+    float   w_inverse;      /* 0.3, losses.py:116                                                   */
+    float   w_depth;        /* l_depth_consist_weight if l_depth_consist else 0, losses.py:114,121  */
+    int64_t n_min_pixels;   /* B*H*W: the mean of losses.py:132                                     */
+} tcsfm_frame_cfg;
+
 /* out_sum[0] = sum_i min_j base[j*stride + i], j < count, i < n  (losses.py:129-131). */
 int tcsfm_min_reduce(const float* base, int64_t stride, int count, int64_t n, float* out_sum, void* stream);
+/* tcsfm_min_reduce + tcsfm_frame_finalize as one launch: the last block to add its partial sum computes the loss
+ * terms.  ticket [1]: scratch. */
+int tcsfm_min_reduce_finalize(const float* base, int64_t stride, int count, int64_t n, float* out_sum, int* ticket,
+                              const float* sums, const tcsfm_frame_cfg* cfg, float* out, float* total, void* stream);
 
 /* Near-ties of that minimum: the same sum, plus (tie_list [capacity], tie_count [1], both device int32) the flat
  * indices i whose two smallest candidates differ by less than `band` (or involve a NaN).  tcsfm_pair_tie_resolve
@@ -273,19 +285,14 @@ int tcsfm_pair_tie_resolve(const tcsfm_pair_group* groups, int n_groups, int B, 
 /* The two calls above as ONE launch (no tie list in global memory): every block takes the min of its pixels,
  * keeps its near-ties in shared memory and re-evaluates them with the exact arithmetic right away.  out_sum [1]:
  * sum over the B*H*W pixels of the min over the groups' diff_img (values as the forward produced them);
- * tie_count [1]: number of pixels re-evaluated (diagnostics).  Replaces torch.min(reconstruction_errors, 1)[0]
+ * counters [2]: (number of pixels re-evaluated, scratch).  With `cfg` != NULL the last block to finish also does
+ * tcsfm_frame_finalize(sums, out_sum, cfg, out_terms, out_total).  Replaces torch.min(reconstruction_errors, 1)[0]
  * of losses.py:129-131 under the fast arithmetic. */
 int tcsfm_pair_min_resolve(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
-                           float w_l1, float w_ssim, int flags, float band, float* out_sum, int* tie_count,
+                           float w_l1, float w_ssim, int flags, float band, float* out_sum, int* counters,
+                           const float* sums, const tcsfm_frame_cfg* cfg, float* out_terms, float* out_total,
                            void* stream);
 
-typedef struct tcsfm_frame_cfg {
-    int32_t n_groups;       /* pair groups of the launch, in the reference's evaluation order      */
-    int32_t role[8];        /* 0 = inverse reconstruction (scalar, x w_inverse), 1 = forward (min)  */
-    float   w_inverse;      /* 0.3, losses.py:116                                                   */
-    float   w_depth;        /* l_depth_consist_weight if l_depth_consist else 0, losses.py:114,121  */
-    int64_t n_min_pixels;   /* B*H*W: the mean of losses.py:132                                     */
-} tcsfm_frame_cfg;
 
 /* out[3] = (l_reconstruct_inverse, l_reconstruct_forward, l_depth) of one scale, from the pair
  * kernels' sums [G,4] and the min-reduce sum (mean_on_mask's 10000-pixel rule on the device).

@@ -2,7 +2,7 @@
 package loader and by the test-only emulator binding)."""
 import ctypes as C
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 ARITH_CPU = 1 << 0
 AUTO_MASK = 1 << 1
@@ -89,7 +89,8 @@ SIGNATURES = {
     "tcsfm_pair_tie_resolve": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                          C.c_int, _fp, _fp, C.c_int, C.c_void_p]),
     "tcsfm_pair_min_resolve": (C.c_int, [C.POINTER(PairGroup), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
-                                         C.c_int, C.c_float, _fp, _fp, C.c_void_p]),
+                                         C.c_int, C.c_float, _fp, _fp, _fp, C.POINTER(FrameCfg), _fp, _fp, C.c_void_p]),
+    "tcsfm_min_reduce_finalize": (C.c_int, [_fp, _i64, C.c_int, _i64, _fp, _fp, _fp, C.POINTER(FrameCfg), _fp, _fp, C.c_void_p]),
     "tcsfm_frame_finalize": (C.c_int, [_fp, _fp, C.POINTER(FrameCfg), _fp, _fp, C.c_void_p]),
     "tcsfm_frame_bwd_prepare": (C.c_int, [_fp, _fp, C.POINTER(FrameCfg), _fp, _fp, C.c_void_p]),
 }

@@ -339,19 +339,43 @@ def pair_tie_resolve(lib, batch, group_ids, w_l1, w_ssim, flags, tie_list, tie_c
     _timing.count_launch()
 
 
-def pair_min_resolve(lib, batch, group_ids, w_l1, w_ssim, flags):
+def pair_min_resolve(lib, batch, group_ids, w_l1, w_ssim, flags, sums=None, cfg=None):
     """min_reduce_ties + pair_tie_resolve as one launch: returns (sum [1] of the per-pixel min over the listed groups'
     diff_img, tie_count int32 [1]); the groups' diff_img entries at the near-tie pixels now hold the exact
-    arithmetic's values."""
+    arithmetic's values.  With `sums` [G,4] and `cfg` the launch also finalises the frame: the return value gains
+    (terms [3], total [1]) like frame_finalize."""
     sub = (PairGroup * len(group_ids))(*[batch.arr[i] for i in group_ids])
-    out = torch.empty((1,), dtype=torch.float32, device=batch.device)
-    tie_count = torch.empty((1,), dtype=torch.int32, device=batch.device)
-    with _timing.launch("pair_min_resolve", batch.device.type == "cuda"):
+    dev = batch.device
+    out = torch.empty((1,), dtype=torch.float32, device=dev)
+    counters = torch.empty((2,), dtype=torch.int32, device=dev)
+    terms = total = None
+    if cfg is not None:
+        terms = torch.empty((3,), dtype=torch.float32, device=dev)
+        total = torch.empty((1,), dtype=torch.float32, device=dev)
+    with _timing.launch("pair_min_resolve", dev.type == "cuda"):
         rc = lib.tcsfm_pair_min_resolve(sub, len(group_ids), batch.b, batch.h, batch.w, w_l1, w_ssim, flags, TIE_BAND,
-                                        _ptr(out), _ptr(tie_count), batch.stream())
+                                        _ptr(out), _ptr(counters), _ptr(sums) if cfg is not None else None,
+                                        C.byref(cfg) if cfg is not None else None, _ptr(terms), _ptr(total), batch.stream())
     _cabi.check(lib, rc)
     _timing.count_launch()
-    return out, tie_count
+    if cfg is not None:
+        return out, counters[0:1], terms, total
+    return out, counters[0:1]
+
+
+def min_reduce_finalize(lib, first, stride, count, n, sums, cfg):
+    """min_reduce + frame_finalize as one launch: (terms [3], total [1])."""
+    dev = first.device
+    out = torch.empty((1,), dtype=torch.float32, device=dev)
+    ticket = torch.empty((1,), dtype=torch.int32, device=dev)
+    terms = torch.empty((3,), dtype=torch.float32, device=dev)
+    total = torch.empty((1,), dtype=torch.float32, device=dev)
+    with _timing.launch("min_reduce", first.is_cuda):
+        rc = lib.tcsfm_min_reduce_finalize(_ptr(first), stride, count, n, _ptr(out), _ptr(ticket), _ptr(sums), C.byref(cfg),
+                                           _ptr(terms), _ptr(total), _stream(first))
+    _cabi.check(lib, rc)
+    _timing.count_launch()
+    return terms, total
 
 
 def make_frame_cfg(roles, w_inverse, w_depth, n_min_pixels):

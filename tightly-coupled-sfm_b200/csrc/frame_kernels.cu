@@ -373,8 +373,10 @@ u8_to_float_kernel(const unsigned char* __restrict__ src, float* __restrict__ ds
 
 constexpr int kReduceThreads = 256;
 
+// `fin.out` != nullptr: the last block to arrive also turns the sums into the loss terms (frame_finalize_body), so the
+// min-reprojection reduce and the finalize are one launch.
 __global__ void __launch_bounds__(kReduceThreads)
-min_reduce_kernel(const float* __restrict__ base, int64_t stride, int count, int64_t n, float* __restrict__ out) {
+min_reduce_kernel(const float* __restrict__ base, int64_t stride, int count, int64_t n, float* __restrict__ out, FrameFinalize fin) {
     TCSFM_SHARED float red[kReduceThreads / 32];
     float part[1] = {0.f};
     for (int64_t i = (int64_t)blockIdx.x * kReduceThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kReduceThreads) {
@@ -386,6 +388,7 @@ min_reduce_kernel(const float* __restrict__ base, int64_t stride, int count, int
         part[0] += m;
     }
     block_atomic_accumulate<1>(part, red, out, threadIdx.x, kReduceThreads);
+    finalize_by_last_block(fin, out);
 }
 
 // The same sum, plus the list of pixels whose two smallest candidates are closer than `band` (or involve a NaN): the
@@ -433,20 +436,7 @@ min_reduce_ties_kernel(const float* __restrict__ base, int64_t stride, int count
 __global__ void frame_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ min_sum, tcsfm_frame_cfg cfg,
                                       float* __restrict__ out, float* __restrict__ total) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float l_inv = 0.f, l_dep = 0.f;
-    for (int g = 0; g < cfg.n_groups; ++g) {
-        const float s0 = sums[g * 4 + 0], s1 = sums[g * 4 + 1], s2 = sums[g * 4 + 2];
-        const bool enough = s1 > 10000.0f;                       // losses.py:144
-        const float l_rep = enough ? __fdiv_rn(s0, s1) : 0.f;
-        const float l_d = enough ? __fdiv_rn(s2, s1) : 0.f;
-        if (cfg.w_depth != 0.f) l_dep = __fadd_rn(l_dep, __fmul_rn(cfg.w_depth, l_d));          // :114-115,:121-122
-        if (cfg.role[g] == 0) l_inv = __fadd_rn(l_inv, __fmul_rn(cfg.w_inverse, l_rep));        // :116
-    }
-    const float l_fwd = min_sum ? __fdiv_rn(min_sum[0], (float)cfg.n_min_pixels) : 0.f;         // :129-132
-    out[0] = l_inv;
-    out[1] = l_fwd;
-    out[2] = l_dep;
-    if (total) total[0] = __fadd_rn(__fadd_rn(l_inv, l_fwd), l_dep);                            // :134-138
+    frame_finalize_body(sums, min_sum, cfg, out, total);
 }
 
 __global__ void frame_bwd_prepare_kernel(const float* __restrict__ g_out, const float* __restrict__ g_total, tcsfm_frame_cfg cfg,
@@ -579,8 +569,25 @@ extern "C" int tcsfm_min_reduce(const float* base, int64_t stride, int count, in
     int64_t blocks = (n + kReduceThreads * 8 - 1) / (kReduceThreads * 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    TCSFM_LAUNCH(min_reduce_kernel, dim3((unsigned)blocks), dim3(kReduceThreads), 0, stream, base, stride, count, n, out_sum);
+    FrameFinalize fin;
+    memset(&fin, 0, sizeof(fin));
+    TCSFM_LAUNCH(min_reduce_kernel, dim3((unsigned)blocks), dim3(kReduceThreads), 0, stream, base, stride, count, n, out_sum, fin);
     return check_launch("tcsfm_min_reduce");
+}
+
+extern "C" int tcsfm_min_reduce_finalize(const float* base, int64_t stride, int count, int64_t n, float* out_sum, int* ticket,
+                                         const float* sums, const tcsfm_frame_cfg* cfg, float* out, float* total, void* stream) {
+    if (!base || !out_sum || count <= 0 || n <= 0) { set_error("tcsfm_min_reduce_finalize: bad arguments"); return 1; }
+    if (!ticket || !sums || !cfg || !out || cfg->n_groups <= 0 || cfg->n_groups > 8) { set_error("tcsfm_min_reduce_finalize: bad finalize arguments"); return 1; }
+    cudaMemsetAsync(out_sum, 0, sizeof(float), (cudaStream_t)stream);
+    cudaMemsetAsync(ticket, 0, sizeof(int), (cudaStream_t)stream);
+    int64_t blocks = (n + kReduceThreads * 8 - 1) / (kReduceThreads * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    FrameFinalize fin;
+    fin.sums = sums; fin.cfg = *cfg; fin.out = out; fin.total = total; fin.ticket = ticket;
+    TCSFM_LAUNCH(min_reduce_kernel, dim3((unsigned)blocks), dim3(kReduceThreads), 0, stream, base, stride, count, n, out_sum, fin);
+    return check_launch("tcsfm_min_reduce_finalize");
 }
 
 extern "C" int tcsfm_frame_finalize(const float* sums, const float* min_sum, const tcsfm_frame_cfg* cfg, float* out, float* total,

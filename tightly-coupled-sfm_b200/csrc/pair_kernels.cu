@@ -792,7 +792,7 @@ constexpr int kMinResolveThreads = 256, kMinResolvePix = 4;
 template <int F>
 __global__ void __launch_bounds__(kMinResolveThreads)
 min_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, int64_t n_total, float band,
-                   float* __restrict__ out_sum, int* __restrict__ tie_count) {
+                   float* __restrict__ out_sum, int* __restrict__ tie_count, FrameFinalize fin) {
     TCSFM_SHARED float red[kMinResolveThreads / 32];
     TCSFM_SHARED int buf[kMinResolveThreads * kMinResolvePix];
     TCSFM_SHARED int n_buf;
@@ -826,6 +826,7 @@ min_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, int64_t n
         resolve_tie<F>(L, j, live ? buf[e] : 0, sub, live);
     }
     block_atomic_accumulate<1>(part, red, out_sum, threadIdx.x, kMinResolveThreads);
+    finalize_by_last_block(fin, out_sum);          // (optional) the loss terms, by the last block to arrive
 }
 
 #ifndef TCSFM_HOST_EMU
@@ -991,13 +992,16 @@ extern "C" int tcsfm_pair_tie_resolve(const tcsfm_pair_group* groups, int n_grou
     return check_launch("tcsfm_pair_tie_resolve");
 }
 
-/* tcsfm_min_reduce_ties + tcsfm_pair_tie_resolve as one launch (no tie list in global memory): out_sum [1] = the sum
- * over the B*H*W pixels of the min over the groups' diff_img, tie_count [1] = the number of pixels re-evaluated. */
+/* tcsfm_min_reduce_ties + tcsfm_pair_tie_resolve (+ tcsfm_frame_finalize when `cfg` is given) as one launch (no tie list
+ * in global memory): out_sum [1] = the sum over the B*H*W pixels of the min over the groups' diff_img, counters [2] =
+ * (number of pixels re-evaluated, scratch ticket). */
 extern "C" int tcsfm_pair_min_resolve(const tcsfm_pair_group* groups, int n_groups, int B, int H, int W,
-                                      float w_l1, float w_ssim, int flags, float band, float* out_sum, int* tie_count,
+                                      float w_l1, float w_ssim, int flags, float band, float* out_sum, int* counters,
+                                      const float* sums, const tcsfm_frame_cfg* cfg, float* out_terms, float* out_total,
                                       void* stream) {
     if (!groups || n_groups <= 0 || n_groups > kMaxGroups) { set_error("tcsfm_pair_min_resolve: 1..%d groups", kMaxGroups); return 1; }
-    if (!out_sum || !tie_count) { set_error("tcsfm_pair_min_resolve: null output"); return 1; }
+    if (!out_sum || !counters) { set_error("tcsfm_pair_min_resolve: null output"); return 1; }
+    if (cfg && (!sums || !out_terms || cfg->n_groups <= 0 || cfg->n_groups > 8)) { set_error("tcsfm_pair_min_resolve: bad finalize arguments"); return 1; }
     PairLaunch L;
     memset(&L, 0, sizeof(L));
     if (int rc = fill_launch(L, groups, n_groups, B, H, W, w_l1, w_ssim, flags & ~TCSFM_ARITH_FAST, "tcsfm_pair_min_resolve", false)) return rc;
@@ -1006,9 +1010,12 @@ extern "C" int tcsfm_pair_min_resolve(const tcsfm_pair_group* groups, int n_grou
     const int64_t n_total = (int64_t)B * H * W;
     if (n_total >= ((int64_t)1 << 31)) { set_error("tcsfm_pair_min_resolve: more than 2^31 pixels"); return 1; }
     cudaMemsetAsync(out_sum, 0, sizeof(float), (cudaStream_t)stream);
-    cudaMemsetAsync(tie_count, 0, sizeof(int), (cudaStream_t)stream);
+    cudaMemsetAsync(counters, 0, 2 * sizeof(int), (cudaStream_t)stream);
+    FrameFinalize fin;
+    memset(&fin, 0, sizeof(fin));
+    if (cfg) { fin.sums = sums; fin.cfg = *cfg; fin.out = out_terms; fin.total = out_total; fin.ticket = counters + 1; }
     const int per_block = kMinResolveThreads * kMinResolvePix;
     dim3 grid((unsigned)((n_total + per_block - 1) / per_block)), block(kMinResolveThreads);
-    TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(min_resolve_kernel<F>, grid, block, 0, stream, L, n_groups, n_total, band, out_sum, tie_count));
+    TCSFM_DISPATCH_FLAVOUR(flags, TCSFM_LAUNCH(min_resolve_kernel<F>, grid, block, 0, stream, L, n_groups, n_total, band, out_sum, counters, fin));
     return check_launch("tcsfm_pair_min_resolve");
 }

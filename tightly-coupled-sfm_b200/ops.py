@@ -315,18 +315,19 @@ class FrameLossFn(torch.autograd.Function):
             if any(fwd_idx[k + 1] - fwd_idx[k] != step for k in range(len(fwd_idx) - 1)):
                 raise ValueError("forward groups must be evenly spaced")
             n_px = diff[0].numel()
-            min_sum = None
-            if fwd_idx and (flags & _cabi.ARITH_FAST) and len(fwd_idx) > 1:
-                # tolerance-level diff values: the near-ties of the per-pixel min are re-decided with the exact arithmetic
-                # (one launch: per-pixel min, its near-ties kept in shared memory and re-evaluated right away)
-                min_sum, tie_count = _raw.pair_min_resolve(lib(), batch, fwd_idx, meta["w_l1"], meta["w_ssim"], flags)
-                global LAST_TIE_COUNT
-                LAST_TIE_COUNT = tie_count
-            elif fwd_idx:
-                min_sum = _raw.min_reduce(lib(), diff[fwd_idx[0]], step * n_px, len(fwd_idx), n_px)
             cfg = _raw.make_frame_cfg([grp[0] for grp in groups], meta["w_inverse"], meta["w_depth"], n_px)
-            # two separate tensors (not views of one buffer): callers may add to `total` in place
-            terms, total = _raw.frame_finalize(lib(), sums, min_sum, cfg)
+            # the per-pixel min over the forward groups and the loss assembly are one launch (the last block of the reduce
+            # finalises); terms / total are two separate tensors (not views of one buffer): callers may add to `total` in place
+            if fwd_idx and (flags & _cabi.ARITH_FAST) and len(fwd_idx) > 1:
+                # tolerance-level diff values: the near-ties of the per-pixel min are kept in shared memory and re-decided
+                # with the exact arithmetic right away
+                global LAST_TIE_COUNT
+                _, LAST_TIE_COUNT, terms, total = _raw.pair_min_resolve(lib(), batch, fwd_idx, meta["w_l1"], meta["w_ssim"], flags,
+                                                                        sums=sums, cfg=cfg)
+            elif fwd_idx:
+                terms, total = _raw.min_reduce_finalize(lib(), diff[fwd_idx[0]], step * n_px, len(fwd_idx), n_px, sums, cfg)
+            else:
+                terms, total = _raw.frame_finalize(lib(), sums, None, cfg)
         if want_grad:
             ctx.save_for_backward(mask, sums, coef, diff, K, *depths, *poses)
             ctx.n_depths, ctx.glued, ctx.pose_stride = len(depths), glued, pose_stride
