@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TCSFM_ABI_VERSION 15
+#define TCSFM_ABI_VERSION 16
 
 /* ---- flags ------------------------------------------------------------------ */
 /* Arithmetic flavour.  Eager PyTorch rounds after every operator, but a few ATen
@@ -220,10 +220,11 @@ int tcsfm_intrinsics_inverse(const float* K, float* kinv, int B, void* stream);
 /* The glue on either side of the pair kernels of one frame (Compute_Loss.forward, losses.py:86-122) as one launch each:
  * prologue = tcsfm_disp_to_depth_fwd of `count` (<= 4) maps of n elements + tcsfm_pose_proj_fwd of n_groups (<= 8) pose
  * tensors [B, >= 6] read in place through a pointer table (row stride `pose_stride` floats; proj [n_groups*B,3,4]);
+ * with `kinv` != NULL the prologue also writes K^-1 [B,9] (tcsfm_intrinsics_inverse);
  * epilogue = the two chain rules (g_pose [n_groups*B,6]). */
 int tcsfm_frame_prologue(const float* const* disp, float* const* depth, int count, int64_t n, float min_disp, float range,
                          const float* const* pose, int n_groups, int pose_stride, float sign, const float* K, int B,
-                         float* proj, int flags, void* stream);
+                         float* proj, float* kinv, int flags, void* stream);
 int tcsfm_frame_epilogue(const float* const* g_depth, const float* const* depth, float* const* g_disp, int count, int64_t n,
                          float range, const float* const* pose, int n_groups, int pose_stride, float sign,
                          const float* K, int B, const float* g_proj, float* g_pose, void* stream);
@@ -304,6 +305,10 @@ int tcsfm_frame_finalize(const float* sums, const float* min_sum, const tcsfm_fr
  * may be NULL) -> g_scalars [G,2] and g_min [1], the upstream scalars tcsfm_pair_loss_bwd consumes. */
 int tcsfm_frame_bwd_prepare(const float* g_out, const float* g_total, const tcsfm_frame_cfg* cfg, float* g_scalars,
                             float* g_min, void* stream);
+/* The same, and the launch also zero-fills `zero` (n_zero floats, 16-byte aligned, n_zero % 4 == 0): the accumulated
+ * depth-gradient buffer of the shared-gradient backward pair launch. */
+int tcsfm_frame_bwd_prepare_zero(const float* g_out, const float* g_total, const tcsfm_frame_cfg* cfg, float* g_scalars,
+                                 float* g_min, float* zero, int64_t n_zero, void* stream);
 
 #ifdef __cplusplus
 }

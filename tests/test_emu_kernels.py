@@ -280,3 +280,36 @@ def test_intrinsics_inverse_has_the_bits_of_torch_on_cuda():
         want = torch.from_numpy(d[fam + "_inv"])
         got = _raw.intrinsics_inverse(emu(), k)
         assert torch.equal(got.view(torch.int32), want.view(torch.int32)), fam
+
+
+def test_frame_prologue_and_epilogue_equal_the_separate_launches():
+    """tcsfm_frame_prologue (disp -> depth + pose -> K[R|t] + K^-1, poses read in place with a row stride) and
+    tcsfm_frame_epilogue (their chain rules) against the single-purpose entry points: identical bits."""
+    from tcsfm_b200 import _raw, synth
+    fr = synth.make_frames(3, 20, 36, seed=2)
+    K = fr["K"]
+    wide = [torch.cat([p, torch.zeros(3, 2)], 1) for p in (fr["poses"][0], fr["poses"][1], fr["poses_inv"][0])]   # [B,8] storage
+    poses = [w[:, 0:6] for w in wide]
+    rows = _raw.pose_rows(poses)
+    assert rows is not None and rows[1] == 8
+    disps = fr["disps"]
+    lo, hi = 1 / synth.KITTI_DEPTH_RANGE[1], 1 / synth.KITTI_DEPTH_RANGE[0]
+    depths, proj, kinv = _raw.frame_prologue(emu(), disps, lo, hi - lo, rows[0], rows[1], K, -1.0, 0, want_kinv=True)
+    want_d = _raw.disp_to_depth_fwd(emu(), disps, lo, hi - lo)
+    want_p = _raw.pose_proj_fwd(emu(), torch.cat(poses, 0).contiguous(), K, -1.0, 0)
+    assert all(torch.equal(a, b) for a, b in zip(depths, want_d))
+    assert torch.equal(proj, want_p)
+    assert torch.equal(kinv, _raw.intrinsics_inverse(emu(), K))
+    g_depths = [torch.randn_like(d) for d in depths]
+    g_proj = torch.randn_like(proj)
+    g_disps, g_pose = _raw.frame_epilogue(emu(), g_depths, depths, hi - lo, rows[0], rows[1], K, -1.0, g_proj)
+    want_gd = _raw.disp_to_depth_bwd(emu(), g_depths, depths, hi - lo)
+    want_gp = _raw.pose_proj_bwd(emu(), torch.cat(poses, 0).contiguous(), K, -1.0, g_proj)
+    assert all(torch.equal(a, b) for a, b in zip(g_disps, want_gd))
+    assert torch.equal(g_pose, want_gp)
+    # prepare + zero-fill in one launch
+    cfg = _raw.make_frame_cfg([0, 1, 0, 1], 0.3, 0.14, 3 * 20 * 36)
+    buf = torch.randn(3, 3, 1, 20, 36)
+    a = _raw.frame_bwd_prepare(emu(), torch.tensor([0.5, 1.0, 2.0]), torch.tensor([0.25]), cfg, zero=buf)
+    b = _raw.frame_bwd_prepare(emu(), torch.tensor([0.5, 1.0, 2.0]), torch.tensor([0.25]), cfg)
+    assert float(buf.abs().sum()) == 0.0 and torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])

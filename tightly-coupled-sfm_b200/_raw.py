@@ -398,28 +398,36 @@ def frame_finalize(lib, sums, min_sum, cfg):
     return out, total
 
 
-def frame_bwd_prepare(lib, g_terms, g_total, cfg):
-    """Upstream of the three terms ([3] or None) and of their sum ([1] or None)."""
+def frame_bwd_prepare(lib, g_terms, g_total, cfg, zero=None):
+    """Upstream of the three terms ([3] or None) and of their sum ([1] or None).  `zero`: a contiguous fp32 buffer the
+    same launch fills with zeros (the accumulated depth gradients of the backward pair launch)."""
     ref = g_terms if g_terms is not None else g_total
     g_terms = None if g_terms is None else _f32c(g_terms, "g_terms")
     g_total = None if g_total is None else _f32c(g_total, "g_total")
     g_scalars = torch.empty((cfg.n_groups, 2), dtype=torch.float32, device=ref.device)
     g_min = torch.empty((1,), dtype=torch.float32, device=ref.device)
     with _timing.launch("frame_bwd_prepare", ref.is_cuda):
-        rc = lib.tcsfm_frame_bwd_prepare(_ptr(g_terms), _ptr(g_total), C.byref(cfg), _ptr(g_scalars), _ptr(g_min), _stream(ref))
+        if zero is not None and zero.numel() % 4 == 0 and zero.data_ptr() % 16 == 0 and zero.is_contiguous():
+            rc = lib.tcsfm_frame_bwd_prepare_zero(_ptr(g_terms), _ptr(g_total), C.byref(cfg), _ptr(g_scalars), _ptr(g_min),
+                                                  _ptr(zero), zero.numel(), _stream(ref))
+        else:
+            if zero is not None:
+                zero.zero_()
+            rc = lib.tcsfm_frame_bwd_prepare(_ptr(g_terms), _ptr(g_total), C.byref(cfg), _ptr(g_scalars), _ptr(g_min), _stream(ref))
     _cabi.check(lib, rc)
     _timing.count_launch()
     return g_scalars, g_min
 
 
 def pair_loss_bwd_shared(lib, batch, mask, sums, coef, g_scalars, g_min, min_info, g_depths, tgt_idx, ref_idx,
-                         w_l1, w_ssim, flags, need_ref_depth_grad):
+                         w_l1, w_ssim, flags, need_ref_depth_grad, zeroed=False):
     """Backward of a multi-group launch whose groups share depth tensors: every group adds into
-    g_depths[tgt_idx[i]] / g_depths[ref_idx[i]] (zero-initialised here).  min_info =
+    g_depths[tgt_idx[i]] / g_depths[ref_idx[i]] (zero-initialised here unless `zeroed`).  min_info =
     (first diff map, stride, [group index -> position or -1], count).  Returns g_proj [G,B,3,4]."""
     g, b, h, w, dev = batch.n, batch.b, batch.h, batch.w, batch.device
     g_proj = torch.empty((g, b, 3, 4), dtype=torch.float32, device=dev)
-    g_depths.zero_()
+    if not zeroed:
+        g_depths.zero_()
     min_first, min_stride, min_pos, min_count = min_info
     for i in range(g):
         a = batch.arr[i]
@@ -554,9 +562,9 @@ def pose_rows(poses):
     return list(poses), stride
 
 
-def frame_prologue(lib, disps, min_disp, disp_range, poses, pose_stride, K, sign, flags):
-    """disp -> depth of <= 4 equally shaped maps and pose -> K[R|t] of the groups' pose tensors as ONE launch.
-    Returns (depths, proj [G*B,3,4])."""
+def frame_prologue(lib, disps, min_disp, disp_range, poses, pose_stride, K, sign, flags, want_kinv=False):
+    """disp -> depth of <= 4 equally shaped maps, pose -> K[R|t] of the groups' pose tensors and (want_kinv) K^-1 as
+    ONE launch.  Returns (depths, proj [G*B,3,4], kinv [B,3,3] or None)."""
     disps = [_f32c(d, "disp") for d in disps]
     if any(d.shape != disps[0].shape for d in disps):
         raise ValueError("frame_prologue: the maps of one launch must share a shape")
@@ -565,12 +573,14 @@ def frame_prologue(lib, disps, min_disp, disp_range, poses, pose_stride, K, sign
     _expect(K, (b, 3, 3), "K")
     depths = [torch.empty_like(d) for d in disps]
     proj = torch.empty((len(poses) * b, 3, 4), dtype=torch.float32, device=K.device)
+    kinv = torch.empty((b, 3, 3), dtype=torch.float32, device=K.device) if want_kinv else None
     with _timing.launch("frame_prologue", K.is_cuda):
         rc = lib.tcsfm_frame_prologue(_ptr_table(disps), _ptr_table(depths), len(disps), disps[0].numel(), min_disp, disp_range,
-                                      _ptr_table(poses), len(poses), pose_stride, sign, _ptr(K), b, _ptr(proj), flags, _stream(K))
+                                      _ptr_table(poses), len(poses), pose_stride, sign, _ptr(K), b, _ptr(proj), _ptr(kinv), flags,
+                                      _stream(K))
     _cabi.check(lib, rc)
     _timing.count_launch()
-    return depths, proj
+    return depths, proj, kinv
 
 
 def frame_epilogue(lib, g_depths, depths, disp_range, poses, pose_stride, K, sign, g_proj):

@@ -141,9 +141,7 @@ __global__ void pose_proj_bwd_kernel(const float* __restrict__ pose, float sign,
 //   getrs: forward substitution y_i = fma(-l_ik, y_k, y_i); backward substitution column by column from the last
 //          (x_2 first, then b_0 takes u_02 x_2 before u_01 x_1), fma updates, IEEE division by the diagonal.
 // One thread per matrix; the output is row-major [B,9], which is what the warp kernels read.
-__global__ void intrinsics_inverse_kernel(const float* __restrict__ K, float* __restrict__ kinv, int B) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+__device__ __forceinline__ void intrinsics_inverse_body(const float* __restrict__ K, float* __restrict__ kinv, int b) {
     float a[3][3];
     int perm[3] = {0, 1, 2};
 #pragma unroll
@@ -187,6 +185,11 @@ __global__ void intrinsics_inverse_kernel(const float* __restrict__ K, float* __
         kinv[b * 9 + 1 * 3 + c] = x1;
         kinv[b * 9 + 2 * 3 + c] = x2;
     }
+}
+
+__global__ void intrinsics_inverse_kernel(const float* __restrict__ K, float* __restrict__ kinv, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) intrinsics_inverse_body(K, kinv, b);
 }
 
 // disp_to_depth (utils/learning_helpers.py:77-86) for up to 4 equally sized maps in one launch:
@@ -273,6 +276,7 @@ struct FrameGlue {
     const float* pose[8];
     const float* K;
     float* proj;
+    float* kinv;             // prologue: K^-1 [Bk,9] out (nullable)
     const float* g_proj;
     float* g_pose;
 };
@@ -282,6 +286,9 @@ __global__ void __launch_bounds__(256) frame_prologue_kernel(const __grid_consta
     if ((int)blockIdx.x < G.nb_maps) { disp_to_depth_fwd_body<kVec>(G.M, G.n, G.min_disp, G.range, blockIdx.x); return; }
     const int i = ((int)blockIdx.x - G.nb_maps) * 256 + threadIdx.x;
     if (i < G.N) pose_proj_fwd_body<kNoFma>(G.pose[i / G.per] + (i % G.per) * G.pose_stride, G.sign, G.K, G.Bk, G.proj, i);
+    // K^-1 by the last threads of the pose blocks (the first ones hold a pose each), hidden behind the map blocks
+    const int j = (int)(gridDim.x - G.nb_maps) * 256 - 1 - i;
+    if (G.kinv && j < G.Bk) intrinsics_inverse_body(G.K, G.kinv, j);
 }
 
 template <int kVec>
@@ -439,8 +446,14 @@ __global__ void frame_finalize_kernel(const float* __restrict__ sums, const floa
     frame_finalize_body(sums, min_sum, cfg, out, total);
 }
 
-__global__ void frame_bwd_prepare_kernel(const float* __restrict__ g_out, const float* __restrict__ g_total, tcsfm_frame_cfg cfg,
-                                         float* __restrict__ g_scalars, float* __restrict__ g_min) {
+// The upstream of the three terms / of their sum -> per-group scalars, by one thread; the other threads of the grid zero
+// the accumulated gradient buffer of the backward pair launch (`zero`, n4 float4 elements; nullable), so that the
+// backward needs no separate fill.
+__global__ void __launch_bounds__(256)
+frame_bwd_prepare_kernel(const float* __restrict__ g_out, const float* __restrict__ g_total, tcsfm_frame_cfg cfg,
+                         float* __restrict__ g_scalars, float* __restrict__ g_min, float4* __restrict__ zero, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256)
+        zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const float gt = g_total ? g_total[0] : 0.f;
     const float g_inv = (g_out ? g_out[0] : 0.f) + gt, g_fwd = (g_out ? g_out[1] : 0.f) + gt, g_dep = (g_out ? g_out[2] : 0.f) + gt;
@@ -600,8 +613,20 @@ extern "C" int tcsfm_frame_finalize(const float* sums, const float* min_sum, con
 extern "C" int tcsfm_frame_bwd_prepare(const float* g_out, const float* g_total, const tcsfm_frame_cfg* cfg, float* g_scalars,
                                        float* g_min, void* stream) {
     if ((!g_out && !g_total) || !cfg || !g_scalars || !g_min || cfg->n_groups <= 0 || cfg->n_groups > 8) { set_error("tcsfm_frame_bwd_prepare: bad arguments"); return 1; }
-    TCSFM_LAUNCH(frame_bwd_prepare_kernel, dim3(1), dim3(32), 0, stream, g_out, g_total, *cfg, g_scalars, g_min);
+    TCSFM_LAUNCH(frame_bwd_prepare_kernel, dim3(1), dim3(256), 0, stream, g_out, g_total, *cfg, g_scalars, g_min, (float4*)nullptr, (int64_t)0);
     return check_launch("tcsfm_frame_bwd_prepare");
+}
+
+extern "C" int tcsfm_frame_bwd_prepare_zero(const float* g_out, const float* g_total, const tcsfm_frame_cfg* cfg, float* g_scalars,
+                                            float* g_min, float* zero, int64_t n_zero, void* stream) {
+    if ((!g_out && !g_total) || !cfg || !g_scalars || !g_min || cfg->n_groups <= 0 || cfg->n_groups > 8) { set_error("tcsfm_frame_bwd_prepare_zero: bad arguments"); return 1; }
+    if (!zero || n_zero <= 0 || n_zero % 4 || ((uintptr_t)zero & 15)) { set_error("tcsfm_frame_bwd_prepare_zero: the buffer must be 16-byte aligned with a multiple of 4 elements"); return 1; }
+    const int64_t n4 = n_zero / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    TCSFM_LAUNCH(frame_bwd_prepare_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, g_out, g_total, *cfg, g_scalars, g_min,
+                 reinterpret_cast<float4*>(zero), n4);
+    return check_launch("tcsfm_frame_bwd_prepare_zero");
 }
 
 
@@ -624,13 +649,13 @@ static int fill_glue(FrameGlue& G, int count, int64_t n, const float* const* pos
 
 extern "C" int tcsfm_frame_prologue(const float* const* disp, float* const* depth, int count, int64_t n, float min_disp, float range,
                                     const float* const* pose, int n_groups, int pose_stride, float sign, const float* K, int B,
-                                    float* proj, int flags, void* stream) {
+                                    float* proj, float* kinv, int flags, void* stream) {
     FrameGlue G;
     memset(&G, 0, sizeof(G));
     if (!disp || !depth || !proj) { set_error("tcsfm_frame_prologue: null pointer"); return 1; }
     if (int rc = fill_glue(G, count, n, pose, n_groups, pose_stride, sign, K, B, "tcsfm_frame_prologue")) return rc;
     for (int k = 0; k < count; ++k) { G.M.in[k] = disp[k]; G.M.out[k] = depth[k]; }
-    G.min_disp = min_disp; G.range = range; G.proj = proj;
+    G.min_disp = min_disp; G.range = range; G.proj = proj; G.kinv = kinv;
     const bool vec = maps_vectorisable(G.M, n);
     G.nb_maps = (int)(((vec ? n / 4 : n) + 255) / 256);
     dim3 grid(G.nb_maps + (G.N + 255) / 256), block(256);

@@ -783,11 +783,11 @@ tie_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, const int
 }
 
 // Per-pixel min over the competing forward groups (losses.py:129-132) and the exact re-evaluation of its near-ties in
-// ONE launch: a block takes the min of its 1024 pixels (sum -> out_sum), collects the pixels whose two best
+// ONE launch: a block takes the min of its 2048 pixels (sum -> out_sum), collects the pixels whose two best
 // candidates are closer than `band` (or involve a NaN) in shared memory and then re-evaluates exactly those with
 // the exact arithmetic, sixteen lanes per (pixel, group), overwriting the groups' diff_img entries before any
 // backward pass reads the routing.  The sum is the one of the values as the forward produced them.
-constexpr int kMinResolveThreads = 256, kMinResolvePix = 4;
+constexpr int kMinResolveThreads = 256, kMinResolvePix = 8;      // 2048 pixels per block: config 2 is one wave of 480 blocks
 
 template <int F>
 __global__ void __launch_bounds__(kMinResolveThreads)
@@ -820,6 +820,7 @@ min_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, int64_t n
     if (threadIdx.x == 0 && ties) atomicAdd(tie_count, ties);
     const int n_tasks = ties * n_groups, sub = threadIdx.x & 15;
     for (int t0 = 0; t0 < n_tasks; t0 += kMinResolveThreads / 16) {
+        if (t0 + (threadIdx.x >> 5) * 2 >= n_tasks) continue;      // both tasks of this warp are past the end (warp-uniform)
         const int task = t0 + (threadIdx.x >> 4);
         const bool live = task < n_tasks;
         const int e = live ? task / n_groups : 0, j = live ? task - e * n_groups : 0;

@@ -130,12 +130,13 @@ class Compute_Loss(nn.modules.Module):
                 # disparities [B,1,h,w] of one scale share a resolution (possibly lower than the images')
                 and all(s[k].dim() == 4 and s[k].shape == specs[0][2].shape for s in specs for k in (2, 3)))
 
-    def _frame_terms(self, specs, roles, intrinsics, kinv, kinv_ready=None):
+    def _frame_terms(self, specs, roles, intrinsics, kinv):
         """All pair evaluations of one scale plus disp_to_depth, the pose algebra and the
         min-reprojection / mean-on-mask reductions as one fused autograd node.  `specs` are
         (tgt_img, ref_img, tgt_disp, ref_disp, pose) with the disparities at their own pyramid
-        resolution and the un-negated poses.  Returns (terms [3], total [1]): (l_reconstruct_inverse,
-        l_reconstruct_forward, l_depth) and their sum."""
+        resolution and the un-negated poses.  kinv = None: K^-1 (models/stn.py:257) is computed inside
+        the node's first launch.  Returns (terms [3], total [1], kinv): (l_reconstruct_inverse,
+        l_reconstruct_forward, l_depth), their sum, and the K^-1 the node used (for the next scale)."""
         images, disps = [], []
 
         def index(lst, t):
@@ -153,10 +154,11 @@ class Compute_Loss(nn.modules.Module):
                 "flags": _pair_flags(self.config), "w_inverse": 0.3,
                 "w_depth": float(self.l_depth_consist_weight) if want_depth else 0.0,
                 "min_depth": self.config['min_depth'], "max_depth": self.config['max_depth'],
-                "n_img": len(images), "groups": groups, "kinv_ready": kinv_ready}
+                "n_img": len(images), "groups": groups}
         # check_sizes accepts [B,8] pose vectors (models/stn.py:252); only the first six enter the warp
         poses = [s[4] if s[4].shape[1] == 6 else s[4][:, 0:6] for s in specs]
-        return ops.FrameLossFn.apply(meta, kinv, intrinsics, *poses, *images, *disps)
+        terms, total = ops.FrameLossFn.apply(meta, kinv, intrinsics, *poses, *images, *disps)
+        return terms, total, meta["kinv"]
 
     def forward(self, source_imgs, target_img, poses, disparity, intrinsics, pose_vec_weight=None,
                 validate=False, epoch=5, target_img_right=None):
@@ -170,7 +172,7 @@ class Compute_Loss(nn.modules.Module):
         # the kernel's sum is the whole `total` only when this call evaluates exactly one scale and divides
         # by one (the reference loops over every entry of `disparity` whatever num_scales says, losses.py:84,136)
         single_scale = len(disparity[0]) == 1 and self.num_scales == 1
-        kinv, kinv_ready = None, None
+        kinv = None
         disparity, source_disparities = disparity[0], disparity[1:]
         poses, poses_inv = poses[0], poses[1]
         _, _, h, w = target_img.size()
@@ -205,10 +207,8 @@ class Compute_Loss(nn.modules.Module):
                     roles.append('fwd')
                 if self._can_fuse_frame(specs, intrinsics):
                     self._refuse_image_grads(specs)
-                    if kinv is None:                                     # models/stn.py:257, once per call, on a side stream
-                        kinv, kinv_ready = inverse_intrinsics_forked(intrinsics)
-                    terms, total = self._frame_terms(specs, roles, intrinsics, kinv, kinv_ready)
-                    kinv_ready = None                                    # the main stream has joined
+                    # K^-1 (models/stn.py:257) once per call: the first fused scale computes it inside its prologue launch
+                    terms, total, kinv = self._frame_terms(specs, roles, intrinsics, kinv)
                     fresh = scale == 0          # 0 + x == x: skip the add into the zero tensor
                     for i, key in enumerate(keys[:3]):
                         losses[key] = terms[i:i + 1] if fresh else losses[key] + terms[i:i + 1]

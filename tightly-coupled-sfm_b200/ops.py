@@ -285,7 +285,9 @@ class FrameLossFn(torch.autograd.Function):
         flags = meta["flags"] | pair_flags(b, images[0].shape[2], images[0].shape[3])
         min_disp, max_disp = 1 / meta["max_depth"], 1 / meta["min_depth"]      # learning_helpers.py:82-83
         with _guard(K):
-            kinv = kinv.contiguous()
+            want_kinv = kinv is None               # models/stn.py:257: computed here, once, and handed back in meta["kinv"]
+            if not want_kinv:
+                kinv = kinv.contiguous()
             # disparities of a lower pyramid scale arrive at their own resolution: the nearest upsample of
             # losses.py:86-87,102-103 happens inside the disp -> depth kernel
             full_hw = tuple(images[0].shape[-2:])
@@ -295,14 +297,20 @@ class FrameLossFn(torch.autograd.Function):
             if glued:
                 # full-resolution disparities, poses readable in place: disp -> depth and pose -> K[R|t] in one launch
                 poses, pose_stride = rows
-                depths, proj = _raw.frame_prologue(lib(), disps, min_disp, max_disp - min_disp, poses, pose_stride, K, -1.0,
-                                                   pose_flags(b))
+                fused_kinv = want_kinv and K.is_cuda
+                depths, proj, k_out = _raw.frame_prologue(lib(), disps, min_disp, max_disp - min_disp, poses, pose_stride, K, -1.0,
+                                                          pose_flags(b), want_kinv=fused_kinv)
+                if fused_kinv:
+                    kinv, want_kinv = k_out, False
             else:
                 depths = []
                 for i in range(0, len(disps), 4):
                     depths += _raw.disp_to_depth_fwd(lib(), disps[i:i + 4], min_disp, max_disp - min_disp, out_hw=full_hw)
                 poses, pose_stride = [torch.cat([p[:, 0:6] for p in poses_in], 0)], 6
                 proj = _raw.pose_proj_fwd(lib(), poses[0], K, -1.0, pose_flags(b))
+            if want_kinv:       # CPU tensors (test builds) take torch's LAPACK inverse, whose bits the CPU goldens carry
+                kinv = _raw.intrinsics_inverse(lib(), K.detach()) if K.is_cuda else torch.linalg.inv_ex(K.detach())[0].contiguous()
+            meta["kinv"] = kinv
             specs = [{"tgt_img": images[ti], "ref_img": images[ri], "tgt_depth": depths[td], "ref_depth": depths[rd],
                       "kinv": kinv, "proj": proj[i * b:(i + 1) * b]} for i, (_, ti, ri, td, rd) in enumerate(groups)]
             batch = _raw.PairBatch(specs)
@@ -350,14 +358,14 @@ class FrameLossFn(torch.autograd.Function):
         fwd_idx, stride = ctx.min_info
         need_ref = (ctx.flags & (_cabi.DEPTH_MASK | _cabi.DEPTH_CONSIST)) != 0
         with _guard(K):
-            g_scalars, g_min = _raw.frame_bwd_prepare(lib(), g_terms, g_total, ctx.cfg)
             g_depths = torch.empty((len(depths),) + tuple(depths[0].shape), dtype=torch.float32, device=K.device)
+            g_scalars, g_min = _raw.frame_bwd_prepare(lib(), g_terms, g_total, ctx.cfg, zero=g_depths)    # also zeroes g_depths
             min_pos = [fwd_idx.index(i) if i in fwd_idx else -1 for i in range(g)]
             min_first = diff[fwd_idx[0]] if fwd_idx else None
             g_proj = _raw.pair_loss_bwd_shared(
                 lib(), ctx.batch, mask, sums, coef, g_scalars, g_min, (min_first, stride, min_pos, len(fwd_idx)),
                 g_depths, [grp[3] for grp in groups], [grp[4] for grp in groups],
-                meta["w_l1"], meta["w_ssim"], ctx.flags, need_ref)
+                meta["w_l1"], meta["w_ssim"], ctx.flags, need_ref, zeroed=True)
             if ctx.glued:                       # the two chain rules behind the pair kernel in one launch
                 g_disps, g_pose = _raw.frame_epilogue(lib(), [g_depths[j] for j in range(len(depths))], depths, ctx.disp_range,
                                                       poses, ctx.pose_stride, K, -1.0, g_proj.reshape(-1, 3, 4))
