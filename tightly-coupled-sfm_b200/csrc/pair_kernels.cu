@@ -798,21 +798,43 @@ min_resolve_kernel(const __grid_constant__ PairLaunch L, int n_groups, int64_t n
     TCSFM_SHARED int n_buf;
     if (threadIdx.x == 0) n_buf = 0;
     __syncthreads();
+    // every load of a candidate map is in flight before the first comparison (a thread's eight pixels per map)
     float part[1] = {0.f};
+    const int64_t i0 = (int64_t)blockIdx.x * kMinResolvePix * kMinResolveThreads + threadIdx.x;
+    float m[kMinResolvePix], second[kMinResolvePix];
+    bool odd[kMinResolvePix];
+    {
+        const float* first = L.g[0].diff_img;
+#pragma unroll
+        for (int k = 0; k < kMinResolvePix; ++k) {
+            const int64_t i = i0 + k * kMinResolveThreads;
+            m[k] = i < n_total ? __ldg(first + i) : 0.f;
+            second[k] = INFINITY;
+        }
+#pragma unroll
+        for (int k = 0; k < kMinResolvePix; ++k) odd[k] = m[k] != m[k];
+    }
+    for (int j = 1; j < n_groups; ++j) {
+        const float* cand = L.g[j].diff_img;
+        float v[kMinResolvePix];
+#pragma unroll
+        for (int k = 0; k < kMinResolvePix; ++k) {
+            const int64_t i = i0 + k * kMinResolveThreads;
+            v[k] = i < n_total ? __ldg(cand + i) : INFINITY;
+        }
+#pragma unroll
+        for (int k = 0; k < kMinResolvePix; ++k) {
+            odd[k] = odd[k] || v[k] != v[k];
+            if (v[k] < m[k]) { second[k] = m[k]; m[k] = v[k]; }
+            else if (v[k] < second[k]) second[k] = v[k];
+        }
+    }
 #pragma unroll
     for (int k = 0; k < kMinResolvePix; ++k) {
-        const int64_t i = ((int64_t)blockIdx.x * kMinResolvePix + k) * kMinResolveThreads + threadIdx.x;
+        const int64_t i = i0 + k * kMinResolveThreads;
         if (i < n_total) {
-            float m = __ldg(L.g[0].diff_img + i), second = INFINITY;
-            bool odd = m != m;
-            for (int j = 1; j < n_groups; ++j) {
-                const float v = __ldg(L.g[j].diff_img + i);
-                odd = odd || v != v;
-                if (v < m) { second = m; m = v; }
-                else if (v < second) second = v;
-            }
-            part[0] += m;
-            if (n_groups > 1 && (odd || !(second - m >= band))) buf[atomicAdd(&n_buf, 1)] = (int)i;
+            part[0] += m[k];
+            if (n_groups > 1 && (odd[k] || !(second[k] - m[k] >= band))) buf[atomicAdd(&n_buf, 1)] = (int)i;
         }
     }
     __syncthreads();
