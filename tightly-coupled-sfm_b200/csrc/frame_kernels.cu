@@ -382,17 +382,32 @@ constexpr int kReduceThreads = 256;
 
 // `fin.out` != nullptr: the last block to arrive also turns the sums into the loss terms (frame_finalize_body), so the
 // min-reprojection reduce and the finalize are one launch.
+constexpr int kReducePix = 8;       // pixels per thread and sweep: their loads of one candidate map are issued together
+
 __global__ void __launch_bounds__(kReduceThreads)
 min_reduce_kernel(const float* __restrict__ base, int64_t stride, int count, int64_t n, float* __restrict__ out, FrameFinalize fin) {
     TCSFM_SHARED float red[kReduceThreads / 32];
     float part[1] = {0.f};
-    for (int64_t i = (int64_t)blockIdx.x * kReduceThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kReduceThreads) {
-        float m = __ldg(base + i);
-        for (int j = 1; j < count; ++j) {
-            const float v = __ldg(base + j * stride + i);
-            m = (v < m || v != v) ? v : m;          // torch.min: lowest index on ties, NaN propagates
+    const int64_t sweep = (int64_t)gridDim.x * kReduceThreads * kReducePix;
+    for (int64_t i0 = (int64_t)blockIdx.x * kReduceThreads * kReducePix + threadIdx.x; i0 < n; i0 += sweep) {
+        float m[kReducePix];
+#pragma unroll
+        for (int k = 0; k < kReducePix; ++k) {
+            const int64_t i = i0 + k * kReduceThreads;
+            m[k] = i < n ? __ldg(base + i) : 0.f;
         }
-        part[0] += m;
+        for (int j = 1; j < count; ++j) {
+            float v[kReducePix];
+#pragma unroll
+            for (int k = 0; k < kReducePix; ++k) {
+                const int64_t i = i0 + k * kReduceThreads;
+                v[k] = i < n ? __ldg(base + j * stride + i) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < kReducePix; ++k) m[k] = (v[k] < m[k] || v[k] != v[k]) ? v[k] : m[k];   // torch.min: lowest index on ties, NaN propagates
+        }
+#pragma unroll
+        for (int k = 0; k < kReducePix; ++k) part[0] += m[k];         // (pixels past the end contributed min(0, 0) = 0)
     }
     block_atomic_accumulate<1>(part, red, out, threadIdx.x, kReduceThreads);
     finalize_by_last_block(fin, out);
