@@ -15,10 +15,10 @@ constexpr int kWarpThreads = 256;
 #endif
 constexpr int kWarpBwdPix = TCSFM_WARP_BWD_PIX;
 #ifndef TCSFM_WARP_BWD_BLOCKS
-#define TCSFM_WARP_BWD_BLOCKS 5     // latency bound (ncu: long scoreboard 60 %): 5 CTAs/SM at 48 registers beat 3 at 80 by 11 %
-#endif
+#define TCSFM_WARP_BWD_BLOCKS 3     // staged loads (every upstream value, then every gather of a pixel in flight together) want 80
+#endif                              // registers: 3 CTAs/SM + two pixels unrolled beat the unstaged 5 CTAs/SM at 48 registers by 6-12 %
 #ifndef TCSFM_WARP_BWD_UNROLL
-#define TCSFM_WARP_BWD_UNROLL 1
+#define TCSFM_WARP_BWD_UNROLL 2
 #endif
 constexpr int kWarpBwdUnroll = TCSFM_WARP_BWD_UNROLL;
 
@@ -98,6 +98,42 @@ warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int img_sc,
         if (k + 1 < kWarpBwdPix) dep_next = (pix + kWarpThreads < n) ? __ldg(dep_b + pix + kWarpThreads) : 1.0f;
 #endif
         const int v = pix / A.W, u = pix - v * A.W;
+#ifndef TCSFM_WARP_BWD_UNSTAGED       // (tuning builds: the per-channel interleaved form)
+        // stage 0: every upstream value (none depends on the geometry) is requested before the projection ...
+        const bool img_up = goimg_b || gostk_b;
+        float gch[3] = {0.f, 0.f, 0.f}, gst[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            if (goimg_b) gch[ch] = __ldg(goimg_b + (ch * n + pix));
+            if (gostk_b) gst[ch] = __ldg(gostk_b + (ch * n + pix));
+        }
+        const float gpd = g_opd ? __ldg(g_opd + (int64_t)b * n + pix) : 0.f;
+        const float g_Z = g_ocd ? __ldg(g_ocd + (int64_t)b * n + pix) : 0.f;
+        WarpPt p;
+        warp_point<F>(c, A, u, v, dep, p);
+        const TapIdx ti = make_taps(p, A.H, A.W);
+        // ... stage 1: all gathers of the pixel in flight together ...
+        Taps tc[3], td;
+        if (img_up) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) tc[ch] = load_taps(img_b, ch * img_sc, ti, A.W);
+        }
+        if (g_opd) td = load_taps(rdep_b, 0, ti, A.W);
+        // ... stage 2: the arithmetic and the scatters
+        float g_ix = 0.f, g_iy = 0.f;
+        if (img_up) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float g = gch[ch] + gst[ch];
+                bilinear_grad(tc[ch], p, g, g_ix, g_iy);
+                if (g_img) scatter_taps(g_img + ((int64_t)b * 3 + ch) * n, 0, ti, g, A.W);
+            }
+        }
+        if (g_opd) {
+            bilinear_grad(td, p, gpd, g_ix, g_iy);
+            if (g_ref_depth) scatter_taps(g_ref_depth + (int64_t)b * n, 0, ti, gpd, A.W);
+        }
+#else
         WarpPt p;
         warp_point<F>(c, A, u, v, dep, p);
         const TapIdx ti = make_taps(p, A.H, A.W);
@@ -119,6 +155,7 @@ warp_bwd_kernel(const float* __restrict__ img, int64_t img_sb, int img_sc,
             if (g_ref_depth) scatter_taps(g_ref_depth + (int64_t)b * n, 0, ti, g, A.W);
         }
         const float g_Z = g_ocd ? __ldg(g_ocd + (int64_t)b * n + pix) : 0.f;
+#endif
         const GeomGrad gg = geom_adjoint(c, A, p, g_ix, g_iy, g_Z);
         if (g_depth) g_depth[(int64_t)b * n + pix] = gg.g_depth;
 #pragma unroll
