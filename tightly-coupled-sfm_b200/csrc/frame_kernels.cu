@@ -467,8 +467,11 @@ __global__ void frame_finalize_kernel(const float* __restrict__ sums, const floa
 __global__ void __launch_bounds__(256)
 frame_bwd_prepare_kernel(const float* __restrict__ g_out, const float* __restrict__ g_total, tcsfm_frame_cfg cfg,
                          float* __restrict__ g_scalars, float* __restrict__ g_min, float4* __restrict__ zero, int64_t n4) {
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256)
-        zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i0 = (int64_t)blockIdx.x * 1024 + threadIdx.x; i0 < n4; i0 += (int64_t)gridDim.x * 1024) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k * 256 < n4) zero[i0 + k * 256] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const float gt = g_total ? g_total[0] : 0.f;
     const float g_inv = (g_out ? g_out[0] : 0.f) + gt, g_fwd = (g_out ? g_out[1] : 0.f) + gt, g_dep = (g_out ? g_out[2] : 0.f) + gt;
@@ -637,8 +640,8 @@ extern "C" int tcsfm_frame_bwd_prepare_zero(const float* g_out, const float* g_t
     if ((!g_out && !g_total) || !cfg || !g_scalars || !g_min || cfg->n_groups <= 0 || cfg->n_groups > 8) { set_error("tcsfm_frame_bwd_prepare_zero: bad arguments"); return 1; }
     if (!zero || n_zero <= 0 || n_zero % 4 || ((uintptr_t)zero & 15)) { set_error("tcsfm_frame_bwd_prepare_zero: the buffer must be 16-byte aligned with a multiple of 4 elements"); return 1; }
     const int64_t n4 = n_zero / 4;
-    int64_t blocks = (n4 + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    int64_t blocks = (n4 + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
     TCSFM_LAUNCH(frame_bwd_prepare_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, g_out, g_total, *cfg, g_scalars, g_min,
                  reinterpret_cast<float4*>(zero), n4);
     return check_launch("tcsfm_frame_bwd_prepare_zero");

@@ -132,15 +132,34 @@ photo_bwd_kernel(const __grid_constant__ PhotoArgs P) {
     const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
     const float* gdiff = P.g_diff ? P.g_diff + (int64_t)b * n : nullptr;
     const float* coef = P.coef + (int64_t)b * kPhotoCoefPlanes * n;
-    for (int cell = threadIdx.x; cell < T1::kCells; cell += kTileThreads) {
-        int cx, cy;
-        T1::cell_xy(cell, cx, cy);
-        const int qx = x0 + cx, qy = y0 + cy;
-        const bool inside = gdiff && qx >= 0 && qx < W && qy >= 0 && qy < H;
-        const int pix = qy * W + qx;
-        const float Gd = inside ? __ldg(gdiff + pix) : 0.f;
+    // two cells per sweep: the twenty loads of both are in flight before the first product is stored
+    for (int cell0 = threadIdx.x; cell0 < T1::kCells; cell0 += 2 * kTileThreads) {
+        int pix[2];
+        bool inside[2];
+        float Gd[2], v[2][9];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) cs[j * T1::kCells + cell] = inside ? Gd * __ldg(coef + (int64_t)j * n + pix) : 0.f;
+        for (int u = 0; u < 2; ++u) {
+            const int cell = cell0 + u * kTileThreads;
+            int cx, cy;
+            T1::cell_xy(cell < T1::kCells ? cell : 0, cx, cy);
+            const int qx = x0 + cx, qy = y0 + cy;
+            inside[u] = cell < T1::kCells && gdiff && qx >= 0 && qx < W && qy >= 0 && qy < H;
+            pix[u] = inside[u] ? qy * W + qx : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            Gd[u] = inside[u] ? __ldg(gdiff + pix[u]) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) v[u][j] = inside[u] ? __ldg(coef + (int64_t)j * n + pix[u]) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int cell = cell0 + u * kTileThreads;
+            if (cell < T1::kCells) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) cs[j * T1::kCells + cell] = Gd[u] * v[u][j];
+            }
+        }
     }
     __syncthreads();
     const int tx = threadIdx.x & (kTileW - 1);
@@ -148,6 +167,20 @@ photo_bwd_kernel(const __grid_constant__ PhotoArgs P) {
     const int gx = x0 + tx;
     const float* tgt = P.tgt + b * P.tgt_sb;
     const float* rec = P.rec + (int64_t)b * 3 * n;
+    // the own pixels' target / reconstruction values and upstream: requested before the window sums
+    float tq[kPixPerThread][3], wq[kPixPerThread][3], gq[kPixPerThread];
+#pragma unroll
+    for (int k = 0; k < kPixPerThread; ++k) {
+        const int gy = y0 + ty0 + k;
+        const bool own = gx < W && gy < H;
+        const int pix = own ? gy * W + gx : 0;
+        gq[k] = (own && gdiff) ? __ldg(gdiff + pix) : 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            tq[k][ch] = own ? __ldg(tgt + ch * P.tgt_sc + pix) : 0.f;
+            wq[k][ch] = own ? __ldg(rec + (int64_t)ch * n + pix) : 0.f;
+        }
+    }
     float h[3][9];
     const bool dup_l = (gx == 1), dup_r = (gx == W - 2);
     auto hsum = [&](int r, float (&out)[9]) {
@@ -172,7 +205,7 @@ photo_bwd_kernel(const __grid_constant__ PhotoArgs P) {
             const bool dup_u = (gy == 1), dup_d = (gy == H - 2);
             const int pix = gy * W + gx;
             const int64_t o = (int64_t)b * n + pix;
-            const float Gd = gdiff ? __ldg(gdiff + pix) : 0.f;
+            const float Gd = gq[k];
             const float gl1 = Gd * A.third * P.w_l1;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
@@ -185,8 +218,7 @@ photo_bwd_kernel(const __grid_constant__ PhotoArgs P) {
                     if (dup_d) s += h[(k + 2) % 3][q];
                     V[j] = s;
                 }
-                const float t = __ldg(tgt + ch * P.tgt_sc + pix);
-                const float w = __ldg(rec + (int64_t)ch * n + pix);
+                const float t = tq[k][ch], w = wq[k][ch];
                 const float dlt = t - w;
                 float gw = V[0] + 2.0f * w * V[1] + t * V[2];
                 if (fabsf(dlt) <= 1.0f) gw += (dlt > 0.f) ? -gl1 : ((dlt < 0.f) ? gl1 : 0.f);
