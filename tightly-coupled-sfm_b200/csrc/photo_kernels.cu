@@ -83,15 +83,36 @@ photo_fwd_kernel(const __grid_constant__ PhotoArgs P) {
     const float* tgt = P.tgt + b * P.tgt_sb;
     const float* src = P.src + b * P.src_sb;
     const float* rec = P.rec + (int64_t)b * 3 * n;
-    for (int cell = threadIdx.x; cell < T1::kCells; cell += kTileThreads) {
-        int ry = 0, rx = 0;
-        const bool ok = T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx);
-        const int pix = ry * W + rx;
+    // two cells per sweep: their eighteen loads are in flight before the first shared-memory store
+    for (int cell0 = threadIdx.x; cell0 < T1::kCells; cell0 += 2 * kTileThreads) {
+        int pix[2];
+        bool ok[2];
+        float t[2][3], r[2][3], sv[2][3];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float t = ok ? __ldg(tgt + ch * P.tgt_sc + pix) : 0.f;
-            tr[ch * T1::kCells + cell] = make_float2(t, ok ? __ldg(rec + (int64_t)ch * n + pix) : 0.f);
-            tsrc[ch * T1::kCells + cell] = make_float2(t, ok ? __ldg(src + ch * P.src_sc + pix) : 0.f);
+        for (int u = 0; u < 2; ++u) {
+            const int cell = cell0 + u * kTileThreads;
+            int ry = 0, rx = 0;
+            ok[u] = cell < T1::kCells && T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx);
+            pix[u] = ok[u] ? ry * W + rx : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                t[u][ch] = ok[u] ? __ldg(tgt + ch * P.tgt_sc + pix[u]) : 0.f;
+                r[u][ch] = ok[u] ? __ldg(rec + (int64_t)ch * n + pix[u]) : 0.f;
+                sv[u][ch] = ok[u] ? __ldg(src + ch * P.src_sc + pix[u]) : 0.f;
+            }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int cell = cell0 + u * kTileThreads;
+            if (cell < T1::kCells) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    tr[ch * T1::kCells + cell] = make_float2(t[u][ch], r[u][ch]);
+                    tsrc[ch * T1::kCells + cell] = make_float2(t[u][ch], sv[u][ch]);
+                }
+            }
         }
     }
     __syncthreads();
