@@ -37,13 +37,18 @@ constexpr int kPftThreads = 256;
 // Per pixel of batch element b: the arg-min over the sources and the mask of optimizer.py:49-68.
 struct PftMin { float diff; int idx; float vmin; };
 
+// kS > 0: the number of sources is a compile-time constant, so the loops unroll and every load of a pixel is issued
+// before the first comparison (a run-time bound serialises them: one DRAM round trip per source)
+template <int kS>
 __device__ __forceinline__ PftMin pft_min(const PftArgs& P, int64_t at, int64_t src_stride, bool automask) {
+    const int S = kS > 0 ? kS : P.S;
     PftMin r;
     r.diff = __ldg(P.f_diff + at);
     r.idx = 0;
     float vsum = __ldg(P.f_valid + at);
     float amin = automask ? __ldg(P.f_aerr + at) : 0.f;
-    for (int j = 1; j < P.S; ++j) {
+#pragma unroll
+    for (int j = 1; j < S; ++j) {
         const int64_t o = at + j * src_stride;
         const float v = __ldg(P.f_diff + o);
         // torch.min(dim): the first index holding the minimum wins; a NaN is the minimum
@@ -59,8 +64,10 @@ __device__ __forceinline__ PftMin pft_min(const PftArgs& P, int64_t at, int64_t 
     return r;
 }
 
+template <int kS>
 __global__ void __launch_bounds__(kPftThreads)
 pft_reduce_fwd_kernel(const PftArgs P) {
+    const int S = kS > 0 ? kS : P.S;
     TCSFM_SHARED float red[6 * (kPftThreads / 32)];
     TCSFM_SHARED int last_block;
     const bool argmin = (P.flags & TCSFM_PFT_ARGMIN) != 0, automask = (P.flags & TCSFM_PFT_AUTOMASK) != 0;
@@ -69,11 +76,12 @@ pft_reduce_fwd_kernel(const PftArgs P) {
     float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int64_t at = (int64_t)blockIdx.x * kPftThreads + threadIdx.x; at < total; at += (int64_t)gridDim.x * kPftThreads) {
         if (argmin) {
-            const PftMin m = pft_min(P, at, src_stride, automask);
+            const PftMin m = pft_min<kS>(P, at, src_stride, automask);
             part[0] += m.diff * m.vmin * __ldg(P.f_weight + at);       // weight_mask[0:B]: the first source's
             part[1] += m.vmin;
         }
-        for (int j = 0; j < P.S; ++j) {
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
             const int64_t o = at + j * src_stride;
             const float wf = __ldg(P.f_weight + o);
             if (!argmin) {
@@ -103,7 +111,7 @@ pft_reduce_fwd_kernel(const PftArgs P) {
     if (last_block && threadIdx.x == 0) {
         __threadfence();
         volatile const float* s = P.sums;
-        const float count = (float)((int64_t)P.S * total);
+        const float count = (float)((int64_t)S * total);
         float loss = argmin ? s[0] / s[1] : (0.25f * s[0]) / s[1];
         if (inverse) loss += (0.25f * s[2]) / s[3];
         if (depth) {
@@ -128,7 +136,7 @@ pft_reduce_bwd_kernel(const PftArgs P) {
     for (int64_t at = (int64_t)blockIdx.x * kPftThreads + threadIdx.x; at < total; at += (int64_t)gridDim.x * kPftThreads) {
         PftMin m;
         m.diff = 0.f; m.idx = -1; m.vmin = 0.f;
-        if (argmin) m = pft_min(P, at, src_stride, automask);
+        if (argmin) m = pft_min<0>(P, at, src_stride, automask);
         for (int j = 0; j < P.S; ++j) {
             const int64_t o = at + j * src_stride;
             float gdiff, gw;
@@ -186,7 +194,12 @@ extern "C" int tcsfm_pft_reduce_fwd(const float* f_diff, const float* f_valid, c
     if (int rc = fill_pft(P, "tcsfm_pft_reduce_fwd")) return rc;
     if (!loss) { set_error("tcsfm_pft_reduce_fwd: null loss pointer"); return 1; }
     cudaMemsetAsync(sums, 0, 8 * sizeof(float), (cudaStream_t)stream);
-    TCSFM_LAUNCH(pft_reduce_fwd_kernel, dim3(pft_grid(P)), dim3(kPftThreads), 0, stream, P);
+    switch (S) {
+        case 1: TCSFM_LAUNCH(pft_reduce_fwd_kernel<1>, dim3(pft_grid(P)), dim3(kPftThreads), 0, stream, P); break;
+        case 2: TCSFM_LAUNCH(pft_reduce_fwd_kernel<2>, dim3(pft_grid(P)), dim3(kPftThreads), 0, stream, P); break;
+        case 3: TCSFM_LAUNCH(pft_reduce_fwd_kernel<3>, dim3(pft_grid(P)), dim3(kPftThreads), 0, stream, P); break;
+        default: TCSFM_LAUNCH(pft_reduce_fwd_kernel<0>, dim3(pft_grid(P)), dim3(kPftThreads), 0, stream, P); break;
+    }
     return check_launch("tcsfm_pft_reduce_fwd");
 }
 
