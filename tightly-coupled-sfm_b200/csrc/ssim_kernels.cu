@@ -13,30 +13,6 @@ static const float kC2 = (float)(0.03 * 0.03);
 
 // kMean: instead of the map, accumulate mean(map) into out[0] (`scale` = 1 / element count): the
 // `.mean()` that follows SSIM_Loss in the PFT depth-initialisation term (optimizer.py:89-90)
-// (x, y) tile with its reflect-padded halo -> shared memory; four cells per sweep so that their eight loads are in
-// flight together (one cell per loop trip costs one DRAM round trip per trip)
-template <class T>
-__device__ __forceinline__ void stage_xy_tile(const float* __restrict__ xp, const float* __restrict__ yp, float* xs, float* ys,
-                                              int x0, int y0, int H, int W) {
-    for (int cell0 = threadIdx.x; cell0 < T::kCells; cell0 += 4 * kTileThreads) {
-        float xv[4], yv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int cell = cell0 + u * kTileThreads;
-            int ry = 0, rx = 0;
-            const bool ok = cell < T::kCells && T::cell_to_reflected(cell, x0, y0, H, W, ry, rx);
-            const int64_t at = ok ? (int64_t)ry * W + rx : 0;
-            xv[u] = ok ? __ldg(xp + at) : 0.f;
-            yv[u] = ok ? __ldg(yp + at) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int cell = cell0 + u * kTileThreads;
-            if (cell < T::kCells) { xs[cell] = xv[u]; ys[cell] = yv[u]; }
-        }
-    }
-}
-
 template <bool kMean>
 __global__ void __launch_bounds__(kTileThreads)
 ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
@@ -48,7 +24,12 @@ ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float*
     float* ys = smem + T1::kCells;
     const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
     const int64_t plane = (int64_t)blockIdx.z * H * W;
-    stage_xy_tile<T1>(x + plane, y + plane, xs, ys, x0, y0, H, W);
+    for (int cell = threadIdx.x; cell < T1::kCells; cell += kTileThreads) {
+        int ry, rx;
+        const bool ok = T1::cell_to_reflected(cell, x0, y0, H, W, ry, rx);
+        xs[cell] = ok ? __ldg(x + plane + (int64_t)ry * W + rx) : 0.f;
+        ys[cell] = ok ? __ldg(y + plane + (int64_t)ry * W + rx) : 0.f;
+    }
     __syncthreads();
     float part[1] = {0.f};
 #pragma unroll
@@ -81,7 +62,12 @@ ssim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const 
     float* cC = cB + T1::kCells;
     const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
     const int64_t plane = (int64_t)blockIdx.z * H * W;
-    stage_xy_tile<T2>(x + plane, y + plane, xs, ys, x0, y0, H, W);
+    for (int cell = threadIdx.x; cell < T2::kCells; cell += kTileThreads) {
+        int ry, rx;
+        const bool ok = T2::cell_to_reflected(cell, x0, y0, H, W, ry, rx);
+        xs[cell] = ok ? __ldg(x + plane + (int64_t)ry * W + rx) : 0.f;
+        ys[cell] = ok ? __ldg(y + plane + (int64_t)ry * W + rx) : 0.f;
+    }
     __syncthreads();
     // adjoint coefficients of every output pixel q in the +1 ring (zero outside the image)
     for (int cell = threadIdx.x; cell < T1::kCells; cell += kTileThreads) {
