@@ -565,3 +565,14 @@ def test_pack_slab_views_alias_one_buffer():
     assert all(torch.equal(views[k], tensors[k]) for k in tensors)
     with pytest.raises(TypeError):
         dataformat.pack_slab({"a": torch.zeros(3), "b": torch.zeros(3, dtype=torch.int32)})
+
+
+def test_compute_loss_rejects_a_pose_batch_that_disagrees_with_the_intrinsics(emu_ops):
+    """The fused frame node reads the poses in place through a pointer table: a pose tensor with fewer rows than the
+    intrinsics must be refused before any kernel sees it (the reference fails with a shape error as well)."""
+    from tcsfm_b200 import synth
+    fr = synth.make_frames(2, 24, 40, seed=3)
+    loss = losses.Compute_Loss(goldens.FULL_CFG)
+    short = [p[:1] for p in fr["poses"]]
+    with pytest.raises((ValueError, RuntimeError, AssertionError)):
+        loss(fr["sources"], fr["target"], [short, fr["poses_inv"]], [[d] for d in fr["disps"]], fr["K"])

@@ -571,6 +571,8 @@ def frame_prologue(lib, disps, min_disp, disp_range, poses, pose_stride, K, sign
     K = _f32c(K, "K")
     b = K.shape[0]
     _expect(K, (b, 3, 3), "K")
+    if any(p.shape[0] != b for p in poses) or disps[0].shape[0] != b:
+        raise ValueError("frame_prologue: poses / disparities / intrinsics disagree on the batch size")
     depths = [torch.empty_like(d) for d in disps]
     proj = torch.empty((len(poses) * b, 3, 4), dtype=torch.float32, device=K.device)
     kinv = torch.empty((b, 3, 3), dtype=torch.float32, device=K.device) if want_kinv else None
@@ -588,6 +590,9 @@ def frame_epilogue(lib, g_depths, depths, disp_range, poses, pose_stride, K, sig
     g_depths = [_f32c(g, "g_depth") for g in g_depths]
     K, g_proj = _f32c(K, "K"), _f32c(g_proj, "g_proj")
     b = K.shape[0]
+    _expect(g_proj, (len(poses) * b, 3, 4), "g_proj")
+    if any(p.shape[0] != b for p in poses) or any(g.shape != d.shape for g, d in zip(g_depths, depths)):
+        raise ValueError("frame_epilogue: poses / gradients disagree with the forward's shapes")
     g_disps = [torch.empty_like(d) for d in depths]
     g_pose = torch.empty((len(poses) * b, 6), dtype=torch.float32, device=K.device)
     with _timing.launch("frame_epilogue", K.is_cuda):
